@@ -1,0 +1,703 @@
+// api.cu -- the C ABI of libainmf.so (include/ainmf.h): handle, tables, host RNG, workspace carving and the
+// stage / whole-path entry points.  No torch types, no C++ exceptions across the boundary.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ainmf.h"
+#include "kernels.h"
+
+using namespace ainmf;
+
+namespace {
+
+// ---- host RNG: numpy RandomState(seed).standard_normal --------------------------------------------------
+// MT19937 seeded with init_genrand, 53-bit doubles, polar Box-Muller with the cached second deviate
+// (numpy/random/src/legacy/legacy-distributions.c: legacy_gauss) -- what _initialize_nmf(init='random')
+// draws from ($SP/sklearn/decomposition/_nmf.py:296-307).
+struct Mt19937 {
+    uint32_t mt[624];
+    int pos;
+    explicit Mt19937(uint32_t seed) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        pos = 624;
+    }
+    void refill() {
+        for (int k = 0; k < 624; ++k) {
+            const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+            mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos == 624) refill();
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    double next_double() {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+};
+
+void standard_normal_f32(uint32_t seed, float* out, size_t n) {
+    Mt19937 g(seed);
+    bool has = false;
+    double cached = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        double v;
+        if (has) {
+            v = cached;
+            has = false;
+        } else {
+            double x1, x2, r2;
+            do {
+                x1 = 2.0 * g.next_double() - 1.0;
+                x2 = 2.0 * g.next_double() - 1.0;
+                r2 = x1 * x1 + x2 * x2;
+            } while (r2 >= 1.0 || r2 == 0.0);
+            const double f = sqrt(-2.0 * log(r2) / r2);
+            cached = f * x1;
+            has = true;
+            v = f * x2;
+        }
+        out[i] = (float)v;      // .astype(X.dtype)
+    }
+}
+
+struct Tables {
+    int n_fft = 0;
+    float2* tw_half = nullptr;
+    float2* tw_full = nullptr;
+    float* window = nullptr;
+    float win_sum = 0.f;
+};
+
+struct Normals {
+    uint32_t seed = 0;
+    int K = 0, T = 0, F = 0;
+    float* Hn = nullptr;   // [K][T] device
+    float* Wn = nullptr;   // [F][K] device
+};
+
+char g_create_error[256] = "";
+
+}  // namespace
+
+struct ainmf_context {
+    int device = 0;
+    int n_sm = 148;
+    std::string err;
+    std::vector<Tables> tables;
+    std::vector<Normals> normals;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int* poll_host = nullptr;     // pinned
+    // communicator for the time-frame-sharded mode (NCCL loaded at run time)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+namespace {
+
+int fail(ainmf_handle h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else snprintf(g_create_error, sizeof g_create_error, "%s", buf);
+    return code;
+}
+#define CU(h, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail(h, AINMF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+size_t al256(size_t n) { return (n + 255) / 256 * 256; }
+
+int check_fft(ainmf_handle h, int n_fft, int hop) {
+    if (!is_pow2(n_fft) || n_fft < 64 || n_fft > 4096) return fail(h, AINMF_ERR_INVALID, "n_fft must be a power of two in [64, 4096], got %d", n_fft);
+    if (hop <= 0 || hop % 4 != 0 || n_fft % hop != 0 || n_fft / hop > 8 || n_fft / hop < 1)
+        return fail(h, AINMF_ERR_INVALID, "hop must be a multiple of 4 that divides n_fft with n_fft/hop <= 8, got %d", hop);
+    return 0;
+}
+
+int geometry(long long N, int n_fft, int hop, StftGeom* g) {
+    // scipy: x_ext = zeros(n/2) ++ x ++ zeros(n/2); nadd = (-(len(x_ext) - n) % hop) % n; T = (len + nadd - n)/hop + 1
+    const long long ext = N + 2LL * (n_fft / 2);
+    long long r = (ext - n_fft) % hop;
+    long long nadd = ((hop - r) % hop) % n_fft;
+    const long long T = (ext + nadd - n_fft) / hop + 1;
+    if (T > 0x7fffffff / 2) return -1;
+    g->N = N; g->n_fft = n_fft; g->hop = hop;
+    g->T = (int)T; g->F = n_fft / 2 + 1; g->ldf = round_up(g->F, 4);
+    return 0;
+}
+
+int get_tables(ainmf_handle h, int n_fft, FftTables* out) {
+    for (const Tables& t : h->tables)
+        if (t.n_fft == n_fft) { out->n_fft = n_fft; out->tw_half = t.tw_half; out->tw_full = t.tw_full; out->window = t.window; out->win_sum = t.win_sum; return 0; }
+    const int M = n_fft / 2;
+    std::vector<float2> th(M), tf(M + 1);
+    std::vector<float> w(n_fft);
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < M; ++k) { th[k].x = (float)cos(-2.0 * pi * k / M); th[k].y = (float)sin(-2.0 * pi * k / M); }
+    for (int k = 0; k <= M; ++k) { tf[k].x = (float)cos(-2.0 * pi * k / n_fft); tf[k].y = (float)sin(-2.0 * pi * k / n_fft); }
+    // get_window('hann_periodic') -> general_cosine(n, [0.5, 0.5], sym=False): fac = linspace(-pi, pi, n+1)[:n];
+    // w = 0.5 + 0.5 cos(fac) in float64 ($SP/scipy/signal/windows/_windows.py:56-66), then cast to float32.
+    float wsum = 0.f;
+    {
+        // float32 pairwise-free sum: numpy's pairwise sum of these values is exact (= n/2) for power-of-two n; we
+        // accumulate in double and round once, which gives the same float.
+        double acc = 0.0;
+        for (int j = 0; j < n_fft; ++j) {
+            const double fac = -pi + (2.0 * pi) * (double)j / (double)n_fft;
+            w[j] = (float)(0.5 + 0.5 * cos(fac));
+            acc += (double)w[j];
+        }
+        wsum = (float)acc;
+    }
+    Tables t;
+    t.n_fft = n_fft; t.win_sum = wsum;
+    CU(h, cudaMalloc((void**)&t.tw_half, sizeof(float2) * M));
+    CU(h, cudaMalloc((void**)&t.tw_full, sizeof(float2) * (M + 1)));
+    CU(h, cudaMalloc((void**)&t.window, sizeof(float) * n_fft));
+    CU(h, cudaMemcpy(t.tw_half, th.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(t.tw_full, tf.data(), sizeof(float2) * (M + 1), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(t.window, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+    h->tables.push_back(t);
+    out->n_fft = n_fft; out->tw_half = t.tw_half; out->tw_full = t.tw_full; out->window = t.window; out->win_sum = wsum;
+    return 0;
+}
+
+// Device copies of the normals sklearn would draw for (seed, K, T, F): H (K,T) first, then W (F,K).
+int get_normals(ainmf_handle h, uint32_t seed, int K, int T, int F, const float** Wn, const float** Hn) {
+    for (const Normals& n : h->normals)
+        if (n.seed == seed && n.K == K && n.T == T && n.F == F) { *Wn = n.Wn; *Hn = n.Hn; return 0; }
+    if (h->normals.size() >= 4) {      // small cache: evict the oldest
+        cudaFree(h->normals[0].Hn);
+        cudaFree(h->normals[0].Wn);
+        h->normals.erase(h->normals.begin());
+    }
+    const size_t nH = (size_t)K * T, nW = (size_t)F * K;
+    std::vector<float> z(nH + nW);
+    standard_normal_f32(seed, z.data(), nH + nW);
+    Normals n;
+    n.seed = seed; n.K = K; n.T = T; n.F = F;
+    CU(h, cudaMalloc((void**)&n.Hn, sizeof(float) * nH));
+    CU(h, cudaMalloc((void**)&n.Wn, sizeof(float) * nW));
+    CU(h, cudaMemcpy(n.Hn, z.data(), sizeof(float) * nH, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(n.Wn, z.data() + nH, sizeof(float) * nW, cudaMemcpyHostToDevice));
+    h->normals.push_back(n);
+    *Wn = n.Wn; *Hn = n.Hn;
+    return 0;
+}
+
+int get_scratch(ainmf_handle h, size_t bytes, void** out) {
+    if (bytes > h->scratch_bytes) {
+        if (h->scratch) cudaFree(h->scratch);
+        h->scratch = nullptr; h->scratch_bytes = 0;
+        CU(h, cudaMalloc(&h->scratch, bytes));
+        h->scratch_bytes = bytes;
+    }
+    *out = h->scratch;
+    return 0;
+}
+
+int get_pinned(ainmf_handle h, size_t bytes, void** out) {
+    if (bytes > h->pinned_bytes) {
+        if (h->pinned) cudaFreeHost(h->pinned);
+        h->pinned = nullptr; h->pinned_bytes = 0;
+        CU(h, cudaMallocHost(&h->pinned, bytes));
+        h->pinned_bytes = bytes;
+    }
+    *out = h->pinned;
+    return 0;
+}
+
+// ---- workspace of the whole path ---------------------------------------------------------------------------
+struct Plan {
+    StftGeom g;
+    int B = 0, K = 0, KP = 0;
+    ImputeWork iw;
+    NmfWork nw;
+    size_t off_V = 0, off_Z = 0, off_bad = 0, off_excl = 0, off_idx = 0, off_nbad = 0, off_nexcl = 0, off_fill = 0,
+           off_state = 0, off_W = 0, off_Ht = 0, off_imp = 0, off_nmf = 0, off_notdone = 0, total = 0;
+    long long vz_stride = 0, bad_stride = 0, w_stride = 0, h_stride = 0;
+};
+
+int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
+    if (!p) return fail(h, AINMF_ERR_INVALID, "params is NULL");
+    if (p->batch <= 0) return fail(h, AINMF_ERR_INVALID, "batch must be positive, got %d", p->batch);
+    int rc = check_fft(h, p->n_fft, p->hop);
+    if (rc) return rc;
+    if (p->n_samples < p->n_fft) return fail(h, AINMF_ERR_INVALID, "n_samples (%lld) must be >= n_fft (%d): scipy would shrink nperseg", (long long)p->n_samples, p->n_fft);
+    if (p->rank < 1 || p->rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", p->rank);
+    if (p->max_iter < 1) return fail(h, AINMF_ERR_INVALID, "max_iter must be >= 1");
+    if (!(p->tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "tol must be >= 0");
+    if (p->solver != AINMF_SOLVER_CD) return fail(h, AINMF_ERR_INVALID, "solver %d is not available in this build (CD only)", p->solver);
+    if (p->n_outer < 1) return fail(h, AINMF_ERR_INVALID, "n_outer must be >= 1");
+    if (geometry(p->n_samples, p->n_fft, p->hop, &pl->g)) return fail(h, AINMF_ERR_INVALID, "signal too long");
+    if (p->col_start >= 0) {
+        if (p->col_start < 1 || p->col_end <= p->col_start || p->col_end > pl->g.T)
+            return fail(h, AINMF_ERR_INVALID, "need 1 <= col_start < col_end <= T (%d), got [%d,%d)", pl->g.T, p->col_start, p->col_end);
+    } else {
+        if (p->frac_den <= 0 || p->frac_num < 0 || p->frac_num >= p->frac_den) return fail(h, AINMF_ERR_INVALID, "need 0 <= frac_num < frac_den");
+        if (!(p->threshold > 0.f)) return fail(h, AINMF_ERR_INVALID, "threshold must be positive");
+    }
+    const int B = p->batch, T = pl->g.T, F = pl->g.F, ldf = pl->g.ldf;
+    pl->B = B; pl->K = p->rank; pl->KP = ainmf_padded_rank(p->rank);
+    const int KP = pl->KP;
+    impute_plan(T, &pl->iw);
+    nmf_plan(B, T, F, KP, h->n_sm, &pl->nw);
+    pl->vz_stride = (long long)T * ldf;
+    pl->bad_stride = round_up(T, 16);
+    pl->w_stride = (long long)F * KP;
+    pl->h_stride = (long long)T * KP;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    pl->off_V = take(sizeof(float) * (size_t)B * pl->vz_stride);
+    pl->off_Z = take(sizeof(float2) * (size_t)B * pl->vz_stride);
+    pl->off_bad = take((size_t)B * pl->bad_stride);
+    pl->off_excl = take((size_t)B * pl->bad_stride);
+    pl->off_idx = take(sizeof(int) * (size_t)B * T);
+    pl->off_nbad = take(sizeof(int) * (size_t)B);
+    pl->off_nexcl = take(sizeof(int) * (size_t)B);
+    pl->off_fill = take(sizeof(float) * (size_t)B * ldf);
+    pl->off_state = take(sizeof(ClipState) * (size_t)B);
+    pl->off_W = take(sizeof(float) * (size_t)B * pl->w_stride);
+    pl->off_Ht = take(sizeof(float) * (size_t)B * pl->h_stride);
+    pl->off_imp = take(impute_work_bytes(B, F, pl->iw));
+    pl->off_nmf = take(nmf_work_bytes(B, T, F, KP, pl->nw));
+    pl->off_notdone = take(sizeof(int) * 4);
+    pl->total = o;
+    return 0;
+}
+
+__global__ void count_not_done_kernel(const ClipState* st, int B, int* out) {
+    // single block
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) c += st[b].done ? 0 : 1;
+    if (c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = s_cnt;
+}
+__global__ void status_summary_kernel(const ClipState* st, int B, int* out) {
+    // out[1] = #clips with status 2 (all frames bad), out[2] = #clips with status 0 (work to do)
+    __shared__ int s_a, s_b;
+    if (threadIdx.x == 0) { s_a = 0; s_b = 0; }
+    __syncthreads();
+    int a = 0, w = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) { a += st[b].status == 2; w += st[b].status == 0; }
+    if (a) atomicAdd(&s_a, a);
+    if (w) atomicAdd(&s_b, w);
+    __syncthreads();
+    if (threadIdx.x == 0) { out[1] = s_a; out[2] = s_b; }
+}
+
+// Runs up to max_iter iterations, polling the stop flags every `poll` iterations when tol > 0.
+int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, int max_iter, float tol, int* d_flag,
+                   cudaStream_t s) {
+    const int poll = 8;
+    for (int it = 1; it <= max_iter; ++it) {
+        CU(h, nmf_cd_iterate(prob, nw, it, s));
+        if (tol > 0.f && (it % poll == 0) && it < max_iter) {
+            AINMF_LAUNCH(count_not_done_kernel, dim3(1), dim3(kThreads), 0, s, prob.state, prob.B, d_flag);
+            CU(h, cudaGetLastError());
+            CU(h, cudaMemcpyAsync(h->poll_host, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CU(h, cudaStreamSynchronize(s));
+            if (h->poll_host[0] == 0) break;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* ainmf_version(void) { return "ainmf 0.1 (sm_100a)"; }
+
+void ainmf_params_default(ainmf_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->batch = 1; p->n_samples = 0; p->n_fft = 1024; p->hop = 256; p->rank = 40; p->max_iter = 200; p->tol = 1e-4f;
+    p->solver = AINMF_SOLVER_CD; p->seed = 42; p->threshold = 1e-4f; p->frac_num = 9; p->frac_den = 10;
+    p->col_start = -1; p->col_end = -1; p->n_outer = 1;
+}
+
+int32_t ainmf_padded_rank(int32_t rank) { return rank <= 32 ? 32 : (rank <= 64 ? 64 : 128); }
+
+int ainmf_create(ainmf_handle* out, int device) {
+    if (!out) return fail(nullptr, AINMF_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+#ifndef AINMF_EMU
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return fail(nullptr, AINMF_ERR_NO_DEVICE, "no CUDA device (%s); ainmf has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, AINMF_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+#endif
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, AINMF_ERR_CUDA, "cannot select device %d", device);
+#ifndef AINMF_EMU
+    if (prop.major != 10) return fail(nullptr, AINMF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+#endif
+    ainmf_context* h = new (std::nothrow) ainmf_context();
+    if (!h) return fail(nullptr, AINMF_ERR_INVALID, "out of host memory");
+    h->device = device;
+    h->n_sm = prop.multiProcessorCount;
+    if (cudaMallocHost((void**)&h->poll_host, 64) != cudaSuccess) { delete h; return fail(nullptr, AINMF_ERR_CUDA, "cudaMallocHost failed"); }
+    *out = h;
+    return AINMF_OK;
+}
+
+int ainmf_comm_destroy_internal(ainmf_handle h);
+
+int ainmf_destroy(ainmf_handle h) {
+    if (!h) return AINMF_OK;
+    cudaSetDevice(h->device);
+    ainmf_comm_destroy_internal(h);
+    for (Tables& t : h->tables) { cudaFree(t.tw_half); cudaFree(t.tw_full); cudaFree(t.window); }
+    for (Normals& n : h->normals) { cudaFree(n.Hn); cudaFree(n.Wn); }
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->poll_host) cudaFreeHost(h->poll_host);
+    delete h;
+    return AINMF_OK;
+}
+
+const char* ainmf_last_error(ainmf_handle h) { return h ? h->err.c_str() : g_create_error; }
+
+int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf) {
+    if (!is_pow2(n_fft) || hop <= 0 || n_fft % hop != 0 || n_samples < 1) return AINMF_ERR_INVALID;
+    StftGeom g;
+    if (geometry(n_samples, n_fft, hop, &g)) return AINMF_ERR_INVALID;
+    if (T) *T = g.T;
+    if (F) *F = g.F;
+    if (ldf) *ldf = g.ldf;
+    return AINMF_OK;
+}
+
+int ainmf_stft(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, int32_t n_fft, int32_t hop,
+               float* mag_ft, float* Z_ft, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || batch <= 0) return fail(h, AINMF_ERR_INVALID, "x is NULL or batch <= 0");
+    int rc = check_fft(h, n_fft, hop);
+    if (rc) return rc;
+    if (n_samples < n_fft) return fail(h, AINMF_ERR_INVALID, "n_samples (%lld) must be >= n_fft (%d)", (long long)n_samples, n_fft);
+    StftGeom g;
+    if (geometry(n_samples, n_fft, hop, &g)) return fail(h, AINMF_ERR_INVALID, "signal too long");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    FftTables tb;
+    if ((rc = get_tables(h, n_fft, &tb))) return rc;
+    const long long vz = (long long)g.T * g.ldf;
+    void* scr;
+    if ((rc = get_scratch(h, al256(sizeof(float) * batch * vz) + sizeof(float2) * batch * vz, &scr))) return rc;
+    float* V = (float*)scr;
+    float2* Z = (float2*)((char*)scr + al256(sizeof(float) * batch * vz));
+    CU(h, launch_stft(x, n_samples, 0, n_samples, batch, g, 0, g.T, tb, V, Z, vz, s));
+    if (mag_ft) CU(h, launch_transpose_f32(V, vz, g.ldf, g.T, g.F, mag_ft, (long long)g.F * g.T, g.T, 0, batch, s));
+    if (Z_ft) CU(h, launch_transpose_c64(Z, vz, g.ldf, g.T, g.F, (float2*)Z_ft, (long long)g.F * g.T, g.T, 0, batch, s));
+    return AINMF_OK;
+}
+
+int ainmf_gap_mask(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, int32_t hop, int32_t n_frames,
+                   float threshold, int32_t frac_num, int32_t frac_den, uint8_t* bad, int32_t* bad_idx,
+                   int32_t* n_bad, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || batch <= 0 || n_samples < 1 || hop < 1 || n_frames < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_gap_mask");
+    if (frac_den <= 0 || frac_num < 0) return fail(h, AINMF_ERR_INVALID, "need frac_den > 0 and frac_num >= 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    unsigned char* flags = bad;
+    if (!flags) {
+        void* scr;
+        int rc = get_scratch(h, (size_t)batch * n_frames, &scr);
+        if (rc) return rc;
+        flags = (unsigned char*)scr;
+    }
+    CU(h, launch_gap_mask(x, n_samples, 0, n_samples, batch, n_samples, hop, 0, n_frames, threshold, frac_num, frac_den,
+                          flags, n_frames, s));
+    if (bad_idx && n_bad) CU(h, launch_compact(flags, n_frames, batch, n_frames, bad_idx, n_frames, n_bad, s));
+    else if (bad_idx || n_bad) return fail(h, AINMF_ERR_INVALID, "bad_idx and n_bad must be given together");
+    return AINMF_OK;
+}
+
+int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, int32_t T, int32_t rank,
+                  int32_t max_iter, float tol, int32_t solver, uint32_t seed, const float* W0, const float* H0,
+                  float* W, float* H, float* err, int32_t* n_iter, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!X_ft || batch <= 0 || F < 1 || T < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_nmf_fit");
+    if (rank < 1 || rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", rank);
+    if (max_iter < 1 || !(tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "need max_iter >= 1 and tol >= 0");
+    if (solver != AINMF_SOLVER_CD) return fail(h, AINMF_ERR_INVALID, "solver %d is not available in this build (CD only)", solver);
+    if ((W0 == nullptr) != (H0 == nullptr)) return fail(h, AINMF_ERR_INVALID, "W0 and H0 must be given together");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    const int KP = ainmf_padded_rank(rank), ldf = round_up(F, 4), B = batch;
+    ImputeWork iw;
+    NmfWork nw;
+    impute_plan(T, &iw);
+    nmf_plan(B, T, F, KP, h->n_sm, &nw);
+    const long long xs = (long long)T * ldf, ws = (long long)F * KP, hs = (long long)T * KP;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    const size_t oX = take(sizeof(float) * B * xs), oW = take(sizeof(float) * B * ws), oH = take(sizeof(float) * B * hs);
+    const size_t oS = take(sizeof(ClipState) * B), oI = take(impute_work_bytes(B, F, iw)), oN = take(nmf_work_bytes(B, T, F, KP, nw));
+    const size_t oB = take((size_t)B * round_up(T, 16)), oF = take(64);
+    void* scr;
+    int rc = get_scratch(h, o, &scr);
+    if (rc) return rc;
+    char* base = (char*)scr;
+    NmfProblem pr;
+    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = tol;
+    pr.Xt = (float*)(base + oX); pr.x_stride = xs;
+    pr.W = (float*)(base + oW); pr.w_stride = ws;
+    pr.Ht = (float*)(base + oH); pr.h_stride = hs;
+    pr.state = (ClipState*)(base + oS);
+    impute_carve(base + oI, B, F, &iw);
+    nmf_carve(base + oN, B, T, F, KP, &nw);
+    unsigned char* nobad = (unsigned char*)(base + oB);
+    CU(h, cudaMemsetAsync(nw.counters, 0, sizeof(unsigned) * B, s));
+    CU(h, cudaMemsetAsync(nobad, 0, (size_t)B * round_up(T, 16), s));
+    CU(h, cudaMemsetAsync(pr.state, 0, sizeof(ClipState) * B, s));
+    // (F,T) -> [T][ldf], pad bins zeroed
+    CU(h, launch_transpose_f32(X_ft, (long long)F * T, T, F, T, pr.Xt, xs, ldf, 1, B, s));
+    CU(h, launch_colsums(pr.Xt, xs, ldf, F, T, B, nullptr, 0, iw, s));
+    CU(h, launch_mean(F, T, B, pr.state, iw, s));
+    if (W0) {
+        CU(h, launch_pack_factors(W0, H0, B, F, T, rank, KP, pr.W, ws, pr.Ht, hs, s));
+    } else {
+        const float *Wn, *Hn;
+        if ((rc = get_normals(h, seed, rank, T, F, &Wn, &Hn))) return rc;
+        CU(h, launch_init_factors(Wn, Hn, T, 0, B, F, T, rank, KP, pr.state, pr.W, ws, pr.Ht, hs, s));
+    }
+    if ((rc = run_iterations(h, pr, nw, max_iter, tol, (int*)(base + oF), s))) return rc;
+    CU(h, nmf_finalize(pr, nw, nobad, round_up(T, 16), s));
+    CU(h, launch_unpack_factors(pr.W, ws, pr.Ht, hs, B, F, T, rank, KP, W, H, s));
+    CU(h, launch_export_state(pr.state, B, nullptr, n_iter, err, nullptr, s));
+    return AINMF_OK;
+}
+
+int ainmf_istft(ainmf_handle h, const float* Z_ft, int32_t batch, int32_t T, int32_t n_fft, int32_t hop,
+                int64_t n_samples, float* y, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!Z_ft || !y || batch <= 0) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_istft");
+    int rc = check_fft(h, n_fft, hop);
+    if (rc) return rc;
+    StftGeom g;
+    g.N = n_samples; g.n_fft = n_fft; g.hop = hop; g.T = T; g.F = n_fft / 2 + 1; g.ldf = round_up(g.F, 4);
+    if (T < 1 || n_samples < 1 || n_samples > (long long)(T - 1) * hop)
+        return fail(h, AINMF_ERR_INVALID, "n_samples must be in [1, (T-1)*hop]");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    FftTables tb;
+    if ((rc = get_tables(h, n_fft, &tb))) return rc;
+    const long long vz = (long long)T * g.ldf;
+    const size_t bs = round_up(T, 16);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    const size_t oZ = take(sizeof(float2) * batch * vz), oB = take((size_t)batch * bs), oN = take(sizeof(int) * batch);
+    void* scr;
+    if ((rc = get_scratch(h, o, &scr))) return rc;
+    char* base = (char*)scr;
+    float2* Z = (float2*)(base + oZ);
+    unsigned char* bad = (unsigned char*)(base + oB);
+    int* nb = (int*)(base + oN);
+    CU(h, cudaMemsetAsync(bad, 0, (size_t)batch * bs, s));
+    CU(h, cudaMemsetAsync(nb, 1, sizeof(int) * batch, s));     // non-zero: take the transform path
+    CU(h, launch_transpose_c64((const float2*)Z_ft, (long long)g.F * T, T, g.F, T, Z, vz, g.ldf, 1, batch, s));
+    CU(h, launch_istft(nullptr, Z, vz, bad, bs, nb, nullptr, 0, 0, batch, g, 0, T, tb, y, n_samples, 0, n_samples, T, s));
+    return AINMF_OK;
+}
+
+size_t ainmf_workspace_bytes(ainmf_handle h, const ainmf_params* p) {
+    if (!h) return 0;
+    Plan pl;
+    if (make_plan(h, p, &pl)) return 0;
+    return pl.total;
+}
+
+int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const float* W0, const float* H0, float* y,
+                  int32_t* bad_idx, int32_t* n_bad, float* W, float* H, float* err, int32_t* n_iter,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    Plan pl;
+    int rc = make_plan(h, p, &pl);
+    if (rc) return rc;
+    if (!x || !y) return fail(h, AINMF_ERR_INVALID, "x and y must not be NULL");
+    if ((W0 == nullptr) != (H0 == nullptr)) return fail(h, AINMF_ERR_INVALID, "W0 and H0 must be given together");
+    if (!workspace || workspace_bytes < pl.total)
+        return fail(h, AINMF_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", pl.total, workspace_bytes);
+    if (((uintptr_t)workspace & 255) != 0) return fail(h, AINMF_ERR_INVALID, "workspace must be 256-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    const StftGeom& g = pl.g;
+    const int B = pl.B, T = g.T, F = g.F, ldf = g.ldf, K = pl.K, KP = pl.KP;
+    const long long N = g.N;
+    FftTables tb;
+    if ((rc = get_tables(h, g.n_fft, &tb))) return rc;
+    char* base = (char*)workspace;
+    float* V = (float*)(base + pl.off_V);
+    float2* Z = (float2*)(base + pl.off_Z);
+    unsigned char* bad = (unsigned char*)(base + pl.off_bad);
+    unsigned char* excl = (unsigned char*)(base + pl.off_excl);
+    int* idx = (int*)(base + pl.off_idx);
+    int* d_nbad = (int*)(base + pl.off_nbad);
+    int* d_nexcl = (int*)(base + pl.off_nexcl);
+    float* fill = (float*)(base + pl.off_fill);
+    ClipState* st = (ClipState*)(base + pl.off_state);
+    int* d_flag = (int*)(base + pl.off_notdone);
+    impute_carve(base + pl.off_imp, B, F, &pl.iw);
+    nmf_carve(base + pl.off_nmf, B, T, F, KP, &pl.nw);
+    NmfProblem pr;
+    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = p->tol;
+    pr.Xt = V; pr.x_stride = pl.vz_stride;
+    pr.W = (float*)(base + pl.off_W); pr.w_stride = pl.w_stride;
+    pr.Ht = (float*)(base + pl.off_Ht); pr.h_stride = pl.h_stride;
+    pr.state = st;
+
+    CU(h, cudaMemsetAsync(pl.nw.counters, 0, sizeof(unsigned) * B, s));
+    // a4: STFT
+    CU(h, launch_stft(x, N, 0, N, B, g, 0, T, tb, V, Z, pl.vz_stride, s));
+    // a2/a3: frame mask
+    const unsigned char* excl_flags = bad;
+    const int* d_nex = d_nbad;
+    if (p->col_start >= 0) {
+        CU(h, launch_range_mask(B, T, p->col_start, T, excl, pl.bad_stride, s));       // fill = mean of frames < col_start
+        CU(h, launch_compact(excl, pl.bad_stride, B, T, idx, T, d_nexcl, s));
+        CU(h, launch_range_mask(B, T, p->col_start, p->col_end, bad, pl.bad_stride, s));
+        excl_flags = excl;
+        d_nex = d_nexcl;
+    } else {
+        CU(h, launch_gap_mask(x, N, 0, N, B, N, g.hop, 0, T, p->threshold, p->frac_num, p->frac_den, bad, pl.bad_stride, s));
+    }
+    CU(h, launch_compact(bad, pl.bad_stride, B, T, idx, T, d_nbad, s));
+    // a5: imputation (in place: V becomes X)
+    CU(h, launch_colsums(V, pl.vz_stride, ldf, F, T, B, excl_flags, pl.bad_stride, pl.iw, s));
+    CU(h, launch_fill(V, pl.vz_stride, ldf, F, T, T, B, bad, pl.bad_stride, d_nbad, d_nex, fill, st, pl.iw, s));
+    // one early look at the counts: rejects the undefined all-bad case and skips the fit when nothing is bad
+    AINMF_LAUNCH(status_summary_kernel, dim3(1), dim3(kThreads), 0, s, st, B, d_flag);
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->poll_host, d_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (h->poll_host[1] > 0) return fail(h, AINMF_ERR_ALL_BAD, "%d clip(s) have every frame flagged: the fill spectrum is undefined", h->poll_host[1]);
+    const bool any_work = h->poll_host[2] > 0;
+    if (any_work) {
+        const float *Wn = nullptr, *Hn = nullptr;
+        if (!W0 && (rc = get_normals(h, p->seed, K, T, F, &Wn, &Hn))) return rc;
+        for (int outer = 0; outer < p->n_outer; ++outer) {
+            // a6: initial factors from mean(X) (sklearn draws a fresh RandomState(seed) at every fit)
+            CU(h, launch_colsums(V, pl.vz_stride, ldf, F, T, B, nullptr, 0, pl.iw, s));
+            CU(h, launch_mean(F, T, B, st, pl.iw, s));
+            if (W0) CU(h, launch_pack_factors(W0, H0, B, F, T, K, KP, pr.W, pr.w_stride, pr.Ht, pr.h_stride, s));
+            else CU(h, launch_init_factors(Wn, Hn, T, 0, B, F, T, K, KP, st, pr.W, pr.w_stride, pr.Ht, pr.h_stride, s));
+            // a7: the fit
+            if ((rc = run_iterations(h, pr, pl.nw, p->max_iter, p->tol, d_flag, s))) return rc;
+            // a8 + a9: objective, then bad frames <- (W H) frames
+            CU(h, nmf_finalize(pr, pl.nw, bad, pl.bad_stride, s));
+        }
+    }
+    // a10 + a11: recombine with the corrupted phase, inverse STFT, trim
+    CU(h, launch_istft(V, Z, pl.vz_stride, bad, pl.bad_stride, d_nbad, x, N, 0, B, g, 0, T, tb, y, N, 0, N, T, s));
+    if (bad_idx) CU(h, cudaMemcpyAsync(bad_idx, idx, sizeof(int) * (size_t)B * T, cudaMemcpyDeviceToDevice, s));
+    CU(h, launch_export_state(st, B, n_bad, n_iter, err, nullptr, s));
+    if (any_work) CU(h, launch_unpack_factors(pr.W, pr.w_stride, pr.Ht, pr.h_stride, B, F, T, K, KP, W, H, s));
+    return AINMF_OK;
+}
+
+int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, int32_t* n_bad_host,
+                       float* err_host, int32_t* n_iter_host, size_t max_device_bytes) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
+    CU(h, cudaSetDevice(h->device));
+    ainmf_params one = *p;
+    one.batch = 1;
+    const size_t per_clip_ws = ainmf_workspace_bytes(h, &one);
+    if (per_clip_ws == 0) return AINMF_ERR_INVALID;    // message set by make_plan
+    const long long N = p->n_samples;
+    if (max_device_bytes == 0) {
+#ifndef AINMF_EMU
+        size_t fr = 0, tot = 0;
+        CU(h, cudaMemGetInfo(&fr, &tot));
+        max_device_bytes = (size_t)((double)(fr + h->scratch_bytes) * 0.8);
+#else
+        max_device_bytes = (size_t)1 << 30;
+#endif
+    }
+    const size_t per_clip = per_clip_ws + 2 * sizeof(float) * (size_t)N + 64;
+    long long chunk = (long long)(max_device_bytes / per_clip);
+    if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
+    if (chunk > p->batch) chunk = p->batch;
+    ainmf_params cp = *p;
+    cp.batch = (int32_t)chunk;
+    const size_t ws = ainmf_workspace_bytes(h, &cp);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    const size_t oX = take(sizeof(float) * chunk * N), oY = take(sizeof(float) * chunk * N), oNb = take(sizeof(int) * chunk),
+                 oEr = take(sizeof(float) * chunk), oNi = take(sizeof(int) * chunk), oWs = take(ws);
+    void* scr;
+    int rc = get_scratch(h, o, &scr);
+    if (rc) return rc;
+    char* base = (char*)scr;
+    cudaStream_t s = 0;
+    for (long long b0 = 0; b0 < p->batch; b0 += chunk) {
+        const int nb = (int)((p->batch - b0 < chunk) ? p->batch - b0 : chunk);
+        cp.batch = nb;
+        CU(h, cudaMemcpyAsync(base + oX, x_host + b0 * N, sizeof(float) * (size_t)nb * N, cudaMemcpyHostToDevice, s));
+        rc = ainmf_inpaint(h, &cp, (const float*)(base + oX), nullptr, nullptr, (float*)(base + oY), nullptr,
+                           (int*)(base + oNb), nullptr, nullptr, (float*)(base + oEr), (int*)(base + oNi), base + oWs, ws, s);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY, sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, s));
+        if (n_bad_host) CU(h, cudaMemcpyAsync(n_bad_host + b0, base + oNb, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+        if (err_host) CU(h, cudaMemcpyAsync(err_host + b0, base + oEr, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
+        if (n_iter_host) CU(h, cudaMemcpyAsync(n_iter_host + b0, base + oNi, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    }
+    CU(h, cudaStreamSynchronize(s));
+    return AINMF_OK;
+}
+
+int ainmf_load_pcm16(ainmf_handle h, const int16_t* pcm, int32_t batch, int64_t n_samples, int32_t channels, float* x,
+                     float* peak, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!pcm || !x || batch <= 0 || n_samples < 1 || channels < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_load_pcm16");
+    CU(h, cudaSetDevice(h->device));
+    void* scr;
+    int rc = get_scratch(h, sizeof(int) * batch, &scr);
+    if (rc) return rc;
+    CU(h, launch_load_pcm16(pcm, batch, n_samples, channels, x, (int*)scr, peak, (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pcm, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!y || !pcm || count < 0) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_store_pcm16");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, launch_store_pcm16(y, count, pcm, (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// kernels.h -- host-callable launchers of the ainmf kernels (internal; the public surface is include/ainmf.h).
+#pragma once
+#include "common.cuh"
+
+namespace ainmf {
+
+// ---- tables owned by the handle (device memory) -------------------------------------------------
+struct FftTables {
+    int n_fft = 0;
+    const float2* tw_half = nullptr;   // [n_fft/2]   exp(-2 pi i k / (n_fft/2))
+    const float2* tw_full = nullptr;   // [n_fft/2+1] exp(-2 pi i k / n_fft)
+    const float* window = nullptr;     // [n_fft]     analysis/synthesis window (float32)
+    float win_sum = 0.f;               // float32 sum of the float32 window
+};
+
+struct StftGeom {
+    long long N;     // samples per clip
+    int n_fft, hop;
+    int T, F, ldf;   // frames, bins, leading dimension of the [T][ldf] arrays
+};
+
+// ---- stft.cu ------------------------------------------------------------------------------------
+// V[b][t][f] = |Z|, Z[b][t][f] = STFT (scipy.signal.stft semantics); x is [B][x_stride].
+// t_offset: global index of local frame 0 (time-frame sharding: x points at the shard's first sample
+// minus halo bookkeeping is done by the caller through x_origin): sample index of x[0] in the clip.
+cudaError_t launch_stft(const float* x, long long x_stride, long long x_origin, long long x_avail, int B,
+                        const StftGeom& g,
+                        int t_begin, int t_count, const FftTables& tb, float* V, float2* Z,
+                        long long vz_stride, cudaStream_t s);
+
+// y[b][n] for n in [n_begin, n_begin + n_count): inverse STFT with overlap-add of Z' where
+// Z'[t] = bad[t] ? V[t] * Z[t]/|Z[t]| : Z[t].  Frames are local indices [0, t_count) that correspond
+// to global frames [t_begin, t_begin + t_count); frames outside contribute nothing (caller adds halos).
+// If n_bad[b] == 0 the kernel copies x (the reference returns the input untouched, main4_NMF_gap.py:54).
+cudaError_t launch_istft(const float* V, const float2* Z, long long vz_stride, const unsigned char* bad,
+                         long long bad_stride, const int* n_bad, const float* x, long long x_stride,
+                         long long x_origin, int B, const StftGeom& g, int t_begin, int t_count,
+                         const FftTables& tb, float* y, long long y_stride, long long n_begin,
+                         long long n_count, int T_total, cudaStream_t s);
+
+// ---- mask.cu ------------------------------------------------------------------------------------
+// bad[b][c] for c in [0,T): column predicate of get_gap_mask / get_mask_from_signal.
+cudaError_t launch_gap_mask(const float* x, long long x_stride, long long x_origin, long long x_avail,
+                            int B, long long N, int hop, int t_begin, int T, float thr, int num, int den,
+                            unsigned char* bad, long long bad_stride, cudaStream_t s);
+// bad flags from an explicit column range (main4_NMF.py:74-76).
+cudaError_t launch_range_mask(int B, int T, int col_start, int col_end, unsigned char* bad,
+                              long long bad_stride, cudaStream_t s);
+// ascending indices of set flags + count, one block per clip.
+cudaError_t launch_compact(const unsigned char* bad, long long bad_stride, int B, int T, int* bad_idx,
+                           long long idx_stride, int* n_bad, cudaStream_t s);
+
+// ---- pcm.cu -------------------------------------------------------------------------------------
+cudaError_t launch_load_pcm16(const int16_t* pcm, int B, long long N, int channels, float* x, int* peak_bits,
+                              float* peak, cudaStream_t s);
+cudaError_t launch_store_pcm16(const float* y, long long count, int16_t* pcm, cudaStream_t s);
+// dst[b][c][r] = src[b][r][c] (r < rows, c < cols); with zero_pad the columns rows..ld_dst of dst are zeroed
+cudaError_t launch_transpose_f32(const float* src, long long src_stride, int ld_src, int rows, int cols, float* dst,
+                                 long long dst_stride, int ld_dst, int zero_pad, int B, cudaStream_t s);
+cudaError_t launch_transpose_c64(const float2* src, long long src_stride, int ld_src, int rows, int cols, float2* dst,
+                                 long long dst_stride, int ld_dst, int zero_pad, int B, cudaStream_t s);
+
+// ---- per-clip control block (device) ---------------------------------------------------------------
+struct ClipState {
+    int done;            // 1 once the stop rule fired (or nothing to do); kernels of the iteration skip the clip
+    int n_iter;          // iterations performed (sklearn's n_iter_)
+    int n_bad;           // number of bad frames
+    int status;          // 0 ok, 1 no bad frames (input returned), 2 every frame bad (undefined in the reference)
+    double viol_init;    // violation of iteration 1
+    double viol_last;
+    double sum_x;        // sum of the imputed spectrogram (for the init scale)
+    float mean_x;        // mean of the imputed spectrogram
+    float err;           // ||X - W H||_F
+};
+
+// ---- impute.cu ----------------------------------------------------------------------------------
+struct ImputeWork {
+    int frames_per_chunk = 0, n_chunks = 0;
+    double* colsum = nullptr;    // [B][n_chunks][F]
+    double* sums = nullptr;      // [B][F+1]: per-bin sums and the grand total (the buffer a time-sharded run all-reduces)
+};
+void impute_plan(int T, ImputeWork* wk);
+size_t impute_work_bytes(int B, int F, const ImputeWork& wk);
+void impute_carve(void* base, int B, int F, ImputeWork* wk);
+// sums[b][f] = sum over frames not flagged in `excl` (null: all frames) of V[b][t][f]; sums[b][F] = total
+cudaError_t launch_colsums(const float* V, long long v_stride, int ldf, int F, int T, int B,
+                           const unsigned char* excl, long long excl_stride, const ImputeWork& wk, cudaStream_t s);
+// fill[b][f] = sums[b][f] / (T_total - n_excl[b]); frames flagged in `bad` <- fill (in place: V becomes the
+// NMF input X); state[b] initialised (n_bad, status, done).
+cudaError_t launch_fill(float* V, long long v_stride, int ldf, int F, int T, int T_total, int B,
+                        const unsigned char* bad, long long bad_stride, const int* n_bad, const int* n_excl,
+                        float* fill /*[B][ldf]*/, ClipState* state, const ImputeWork& wk, cudaStream_t s);
+// state[b].mean_x = sums[b][F] / (F*T_total); re-arms the iteration counters
+cudaError_t launch_mean(int F, int T_total, int B, ClipState* state, const ImputeWork& wk, cudaStream_t s);
+// W[b][f][k] = |avg_b * Wn[f][k]|, Ht[b][t][k] = |avg_b * Hn[k][t]|, avg_b = sqrt(mean_x/K) (float32);
+// pad components k >= K are zero.  ($SP/sklearn/decomposition/_nmf.py:296-307)
+cudaError_t launch_init_factors(const float* Wn /*[F][K]*/, const float* Hn /*[K][T_total]*/, int T_total,
+                                int t_begin, int B, int F, int T, int K, int KP, const ClipState* state, float* W,
+                                long long w_stride, float* Ht, long long h_stride, cudaStream_t s);
+// user factors W0[b][F][K], H0[b][K][T] -> padded internal layout
+cudaError_t launch_pack_factors(const float* W0, const float* H0, int B, int F, int T, int K, int KP, float* W,
+                                long long w_stride, float* Ht, long long h_stride, cudaStream_t s);
+// internal -> user layout W[b][F][K], H[b][K][T]
+cudaError_t launch_unpack_factors(const float* W, long long w_stride, const float* Ht, long long h_stride, int B,
+                                  int F, int T, int K, int KP, float* Wout, float* Hout, cudaStream_t s);
+// copy selected ClipState fields into plain arrays (any may be null)
+cudaError_t launch_export_state(const ClipState* st, int B, int* n_bad, int* n_iter, float* err, int* status,
+                                cudaStream_t s);
+// state for a fit on a caller-provided X (no imputation stage): done=0, n_iter=0
+cudaError_t launch_reset_state(ClipState* st, int B, cudaStream_t s);
+
+// ---- nmf_cd.cu ----------------------------------------------------------------------------------
+struct NmfProblem {
+    int B, T, F, ldf, KP;
+    float tol;
+    float* Xt; long long x_stride;      // [B][T][ldf]
+    float* W; long long w_stride;       // [B][F][KP]
+    float* Ht; long long h_stride;      // [B][T][KP]
+    ClipState* state;                   // [B]
+};
+struct NmfWork {
+    int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;
+    float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
+    float *violW = nullptr, *violH = nullptr;
+    unsigned* counters = nullptr;       // must be zero before the first iteration
+    double* err_partial = nullptr;
+};
+void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
+size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk);
+void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
+cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
+// err = ||X - W H||_F into state[b].err, then bad frames of Xt <- (W H) frames
+cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
+                         cudaStream_t s);
+
+}  // namespace ainmf

@@ -1,0 +1,617 @@
+// nmf_cd.cu -- K4: one coordinate-descent NMF iteration as FFMA kernels for sm_100a.
+//
+//   X  = imputed magnitude spectrogram, frame-major Xt[b][t][f] (ldf)          (main4_NMF_gap.py:56-59)
+//   W  [b][f][KP],  Ht [b][t][KP]                                              (KP = padded rank)
+// per iteration ($SP/sklearn/decomposition/_nmf.py:491-516):
+//   HHt = Ht^T Ht           gram_kernel            (deterministic two-stage reduction)
+//   XHt = X Ht              xht_kernel             (split over time, partials reduced in fixed order)
+//   W   <- sweep            w_sweep_kernel
+//   WtW = W^T W             gram_kernel
+//   XtW = X^T W ; Ht <- sweep   h_step_kernel      (fused: the XtW tile never leaves the SM)
+//   stop rule               stop_kernel
+// The spectrogram is read exactly twice per iteration (xht_kernel, h_step_kernel): 8*F*T bytes.
+#include "kernels.h"
+#include "nmf_cd.cuh"
+
+namespace ainmf {
+
+// =====================================================================================================
+// gram: G[b] = A[b]^T A[b] for A [rows][KP]; grid = (P, B); partials then last-block reduce.
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads)
+gram_kernel(const float* __restrict__ A, long long a_stride, int rows, int rows_per_block,
+            float* __restrict__ partial /*[B][P][KP*KP]*/, float* __restrict__ G /*[B][KP*KP]*/,
+            unsigned* __restrict__ counters /*[B]*/, const ClipState* __restrict__ st) {
+    constexpr int TN = KP / 16;
+    constexpr int RB = 32;                               // rows staged per step
+    __shared__ __align__(16) float sA[RB][KP];
+    __shared__ unsigned s_last;
+    const int b = blockIdx.y, p = blockIdx.x, P = gridDim.x;
+    if (st[b].done) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* Ab = A + (long long)b * a_stride;
+    const int r_begin = p * rows_per_block;
+    const int r_end = min(rows, r_begin + rows_per_block);
+    float acc[TN][TN];
+#pragma unroll
+    for (int i = 0; i < TN; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int r0 = r_begin; r0 < r_end; r0 += RB) {
+        for (int i = threadIdx.x; i < RB * KP / 4; i += blockDim.x) {
+            const int rr = (4 * i) / KP, cc = (4 * i) % KP;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + rr < r_end) v = *reinterpret_cast<const float4*>(Ab + (long long)(r0 + rr) * KP + cc);
+            *reinterpret_cast<float4*>(&sA[rr][cc]) = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < RB; ++kk) {
+            float fi[TN], fj[TN];
+            load_frag<TN>(sA[kk], ty, fi);
+            load_frag<TN>(sA[kk], tx, fj);
+#pragma unroll
+            for (int i = 0; i < TN; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(fi[i], fj[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = partial + ((long long)b * P + p) * (KP * KP);
+#pragma unroll
+    for (int i = 0; i < TN; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) out[frag_col<TN>(ty, i) * KP + frag_col<TN>(tx, j)] = acc[i][j];
+
+    // last block of this clip sums the partials in index order (deterministic)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == (unsigned)(P - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const float* pb = partial + (long long)b * P * (KP * KP);
+        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+            float s = 0.f;
+            for (int q = 0; q < P; ++q) s += pb[(long long)q * (KP * KP) + e];
+            G[(long long)b * (KP * KP) + e] = s;
+        }
+        if (threadIdx.x == 0) counters[b] = 0u;          // ready for the next launch
+    }
+}
+
+// =====================================================================================================
+// xht: partial[b][s][f][:] = sum_{t in split s} Xt[t][f] * Ht[t][:];  grid = (ceil(F/128), S, B)
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads)
+xht_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int T,
+           const float* __restrict__ Ht, long long h_stride, int frames_per_split,
+           float* __restrict__ partial /*[B][S][F][KP]*/, const ClipState* __restrict__ st) {
+    constexpr int TN = KP / 16;
+    constexpr int BM = 128, BK = 16;
+    constexpr int A4 = BK * BM / 4 / kThreads;            // float4 per thread for the A tile (=2)
+    constexpr int B4 = (BK * KP / 4 + kThreads - 1) / kThreads;
+    __shared__ __align__(16) float sA[BK][BM];
+    __shared__ __align__(16) float sB[BK][KP];
+    const int b = blockIdx.z, split = blockIdx.y, S = gridDim.y;
+    if (st[b].done) return;
+    const int f0 = blockIdx.x * BM;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int warp = threadIdx.x >> 5;
+    const bool act0 = (f0 + 8 * warp) < F;                // rows 4ty..4ty+3
+    const bool act1 = (f0 + 64 + 8 * warp) < F;           // rows 64+4ty..
+    const float* Xb = Xt + (long long)b * x_stride;
+    const float* Hb = Ht + (long long)b * h_stride;
+    const int t_begin = split * frames_per_split;
+    const int t_end = min(T, t_begin + frames_per_split);
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[A4], rb[B4];
+    auto gload = [&](int t0) {
+#pragma unroll
+        for (int u = 0; u < A4; ++u) {
+            const int i = threadIdx.x + u * kThreads;     // float4 index in the [BK][BM] tile
+            const int kk = i / (BM / 4), m = (i % (BM / 4)) * 4;
+            ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + kk < t_end && f0 + m < ldf)
+                ra[u] = *reinterpret_cast<const float4*>(Xb + (long long)(t0 + kk) * ldf + f0 + m);
+        }
+#pragma unroll
+        for (int u = 0; u < B4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < BK * KP / 4) {
+                const int kk = i / (KP / 4), n = (i % (KP / 4)) * 4;
+                if (t0 + kk < t_end) rb[u] = *reinterpret_cast<const float4*>(Hb + (long long)(t0 + kk) * KP + n);
+            }
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int u = 0; u < A4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            *reinterpret_cast<float4*>(&sA[i / (BM / 4)][(i % (BM / 4)) * 4]) = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < B4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            if (i < BK * KP / 4) *reinterpret_cast<float4*>(&sB[i / (KP / 4)][(i % (KP / 4)) * 4]) = rb[u];
+        }
+    };
+
+    if (t_begin < t_end) gload(t_begin);
+    for (int t0 = t_begin; t0 < t_end; t0 += BK) {
+        sstore();
+        __syncthreads();
+        if (t0 + BK < t_end) gload(t0 + BK);               // prefetch the next tile into registers
+        if (act0 || act1) {
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float fb[TN];
+                load_frag<TN>(sB[kk], tx, fb);
+                if (act0) {
+                    const float4 a = *reinterpret_cast<const float4*>(&sA[kk][4 * ty]);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], fb[j], acc[i][j]);
+                }
+                if (act1) {
+                    const float4 a = *reinterpret_cast<const float4*>(&sA[kk][64 + 4 * ty]);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < TN; ++j) acc[4 + i][j] = fmaf(av[i], fb[j], acc[4 + i][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* out = partial + (((long long)b * S + split) * F) * KP;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int f = f0 + ((i < 4) ? 4 * ty + i : 64 + 4 * ty + (i - 4));
+        if (f < F) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) out[(long long)f * KP + frag_col<TN>(tx, j)] = acc[i][j];
+        }
+    }
+}
+
+// =====================================================================================================
+// w sweep: B = sum_s partial[s]; W <- sweep(W, HHt, B); grid = (ceil(F / (256/L)), B)
+// =====================================================================================================
+template <int KP, int L>
+__global__ void __launch_bounds__(kThreads)
+w_sweep_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
+               const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
+               const ClipState* __restrict__ st) {
+    constexpr int SL = KP / L;
+    constexpr int ROWS = kThreads / L;
+    AINMF_DYN_SMEM(smem_raw);
+    float* sG = reinterpret_cast<float*>(smem_raw);       // [KP][KP + 4L]
+    __shared__ float s_red[32];
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    load_gram_padded<KP, L>(sG, G + (long long)b * KP * KP);
+    const int l = threadIdx.x % L;
+    const int f = blockIdx.x * ROWS + threadIdx.x / L;
+    const bool valid = f < F;
+    float a[SL], bv[SL];
+#pragma unroll
+    for (int q = 0; q < SL; ++q) { a[q] = 0.f; bv[q] = 0.f; }
+    if (valid) {
+        const float* wr = W + (long long)b * w_stride + (long long)f * KP + l * SL;
+#pragma unroll
+        for (int q = 0; q < SL; q += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(wr + q);
+            a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
+        }
+        for (int s = 0; s < S; ++s) {                      // fixed order -> deterministic
+            const float* pr = partial + ((((long long)b * S + s) * F) + f) * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(pr + q);
+                bv[q] += v.x; bv[q + 1] += v.y; bv[q + 2] += v.z; bv[q + 3] += v.w;
+            }
+        }
+    }
+    __syncthreads();
+    const float v = cd_sweep_row<KP, L>(a, bv, sG, l, valid);
+    if (valid) {
+        float* wr = W + (long long)b * w_stride + (long long)f * KP + l * SL;
+#pragma unroll
+        for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(wr + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+    }
+    const float tot = block_sum(v, s_red);
+    if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+}
+
+// =====================================================================================================
+// h step: XtW tile = Xt[tile] W ; Ht[tile] <- sweep(Ht[tile], WtW, XtW tile); grid = (ceil(T/BM), B)
+// =====================================================================================================
+template <int KP, int BM> struct HStepCfg {
+    static constexpr int L = (BM == 32) ? 8 : 4;
+    static constexpr int BK = 32;
+    static constexpr int APITCH = BK + 4;
+    static constexpr int CPITCH = KP + 4;
+    static constexpr int GPITCH = KP + 4 * L;
+    static constexpr int gemm_floats = BM * APITCH + BK * KP;
+    static constexpr int c_floats = BM * CPITCH;
+    static constexpr int work_floats = gemm_floats > c_floats ? gemm_floats : c_floats;
+    static constexpr size_t smem_bytes = sizeof(float) * (size_t)(work_floats + KP * GPITCH);
+};
+
+template <int KP, int BM>
+__global__ void __launch_bounds__(kThreads)
+h_step_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int T,
+              const float* __restrict__ W, long long w_stride, const float* __restrict__ G,
+              float* __restrict__ Ht, long long h_stride, float* __restrict__ viol /*[B][gridDim.x]*/,
+              const ClipState* __restrict__ st) {
+    using Cfg = HStepCfg<KP, BM>;
+    constexpr int TN = KP / 16, TM = BM / 16, L = Cfg::L, SL = KP / L, BK = Cfg::BK;
+    constexpr int APITCH = Cfg::APITCH, CPITCH = Cfg::CPITCH;
+    constexpr int A4 = (BM * BK / 4 + kThreads - 1) / kThreads;
+    constexpr int B4 = (BK * KP / 4 + kThreads - 1) / kThreads;
+    AINMF_DYN_SMEM(smem_raw);
+    float* sA = reinterpret_cast<float*>(smem_raw);        // [BM][APITCH]
+    float* sB = sA + BM * APITCH;                          // [BK][KP]
+    float* sC = sA;                                        // [BM][CPITCH]   (aliases the GEMM tiles)
+    float* sG = sA + Cfg::work_floats;                     // [KP][GPITCH]
+    __shared__ float s_red[32];
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    const int m0 = blockIdx.x * BM;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* Xb = Xt + (long long)b * x_stride;
+    const float* Wb = W + (long long)b * w_stride;
+    load_gram_padded<KP, L>(sG, G + (long long)b * KP * KP);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[A4], rb[B4];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < A4; ++u) {
+            const int i = threadIdx.x + u * kThreads;       // float4 index in the [BM][BK] tile
+            ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < BM * BK / 4) {
+                const int m = i / (BK / 4), kk = (i % (BK / 4)) * 4;
+                if (m0 + m < T && k0 + kk < ldf)
+                    ra[u] = *reinterpret_cast<const float4*>(Xb + (long long)(m0 + m) * ldf + k0 + kk);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < B4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < BK * KP / 4) {
+                const int kk = i / (KP / 4), n = (i % (KP / 4)) * 4;
+                if (k0 + kk < F) rb[u] = *reinterpret_cast<const float4*>(Wb + (long long)(k0 + kk) * KP + n);
+            }
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int u = 0; u < A4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            if (i < BM * BK / 4) *reinterpret_cast<float4*>(sA + (i / (BK / 4)) * APITCH + (i % (BK / 4)) * 4) = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < B4; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            if (i < BK * KP / 4) *reinterpret_cast<float4*>(sB + (i / (KP / 4)) * KP + (i % (KP / 4)) * 4) = rb[u];
+        }
+    };
+
+    gload(0);
+    for (int k0 = 0; k0 < F; k0 += BK) {
+        sstore();
+        __syncthreads();
+        if (k0 + BK < F) gload(k0 + BK);
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            float av[TM][4];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(sA + (ty + 16 * i) * APITCH + k4);
+                av[i][0] = a.x; av[i][1] = a.y; av[i][2] = a.z; av[i][3] = a.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float fb[TN];
+                load_frag<TN>(sB + (k4 + c) * KP, tx, fb);
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i][c], fb[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    // XtW tile -> shared (row = frame within tile)
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) sC[(ty + 16 * i) * CPITCH + frag_col<TN>(tx, j)] = acc[i][j];
+    __syncthreads();
+
+    constexpr int ROWS = kThreads / L;                      // rows swept per pass
+    const int l = threadIdx.x % L;
+    float vsum = 0.f;
+    float* Hb = Ht + (long long)b * h_stride;
+    for (int r0 = 0; r0 < BM; r0 += ROWS) {
+        const int r = r0 + threadIdx.x / L;
+        const int t = m0 + r;
+        const bool valid = (r < BM) && (t < T);
+        float a[SL], bv[SL];
+#pragma unroll
+        for (int q = 0; q < SL; ++q) { a[q] = 0.f; bv[q] = 0.f; }
+        if (valid) {
+            const float* hr = Hb + (long long)t * KP + l * SL;
+            const float* cr = sC + r * CPITCH + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(hr + q);
+                a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
+                const float4 c = *reinterpret_cast<const float4*>(cr + q);
+                bv[q] = c.x; bv[q + 1] = c.y; bv[q + 2] = c.z; bv[q + 3] = c.w;
+            }
+        }
+        vsum += cd_sweep_row<KP, L>(a, bv, sG, l, valid);
+        if (valid) {
+            float* hr = Hb + (long long)t * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(hr + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+        }
+    }
+    const float tot = block_sum(vsum, s_red);
+    if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+}
+
+// =====================================================================================================
+// stop rule: one warp per clip.  it is 1-based.
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, int nW,
+            const float* __restrict__ violH, int nH, int it, float tol) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    if (st[b].done) return;
+    double v = 0.0;
+    for (int i = lane; i < nW; i += 32) v += (double)violW[(long long)b * nW + i];
+    for (int i = lane; i < nH; i += 32) v += (double)violH[(long long)b * nH + i];
+    v = warp_sum_d(v);
+    if (lane == 0) {
+        ClipState s = st[b];
+        s.n_iter = it;
+        if (it == 1) s.viol_init = v;
+        s.viol_last = v;
+        if (s.viol_init == 0.0) s.done = 1;
+        else if (v / s.viol_init <= (double)tol) s.done = 1;
+        st[b] = s;
+    }
+}
+
+// =====================================================================================================
+// finalize: err^2 partial = sum (X - W Ht^T)^2 over a tile of frames; bad frames <- (W Ht^T) row
+// (a8 + a9: _nmf.py:1623 and main4_NMF_gap.py:65-68).  grid = (ceil(T/16), B)
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads)
+finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int T,
+                const float* __restrict__ W, long long w_stride, const float* __restrict__ Ht,
+                long long h_stride, const unsigned char* __restrict__ bad, long long bad_stride,
+                double* __restrict__ err_partial /*[B][gridDim.x]*/) {
+    constexpr int FR = 16;
+    __shared__ __align__(16) float sH[FR][KP];
+    __shared__ unsigned char s_bad[FR];
+    __shared__ double s_red[32];
+    const int b = blockIdx.y, t0 = blockIdx.x * FR;
+    const float* Hb = Ht + (long long)b * h_stride;
+    for (int i = threadIdx.x; i < FR * KP; i += blockDim.x) {
+        const int r = i / KP, c = i % KP;
+        sH[r][c] = (t0 + r < T) ? Hb[(long long)(t0 + r) * KP + c] : 0.f;
+    }
+    if (threadIdx.x < FR) s_bad[threadIdx.x] = (t0 + threadIdx.x < T) ? bad[(long long)b * bad_stride + t0 + threadIdx.x] : 0;
+    __syncthreads();
+    float* Xb = Xt + (long long)b * x_stride;
+    const float* Wb = W + (long long)b * w_stride;
+    double e2 = 0.0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float dot[FR];
+#pragma unroll
+        for (int r = 0; r < FR; ++r) dot[r] = 0.f;
+        const float* wr = Wb + (long long)f * KP;
+        for (int k = 0; k < KP; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+            for (int r = 0; r < FR; ++r) {
+                const float4 h = *reinterpret_cast<const float4*>(&sH[r][k]);
+                dot[r] = fmaf(w.x, h.x, dot[r]);
+                dot[r] = fmaf(w.y, h.y, dot[r]);
+                dot[r] = fmaf(w.z, h.z, dot[r]);
+                dot[r] = fmaf(w.w, h.w, dot[r]);
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+            if (t0 + r < T) {
+                const long long o = (long long)(t0 + r) * ldf + f;
+                const float d = Xb[o] - dot[r];
+                s = fmaf(d, d, s);
+                if (s_bad[r]) Xb[o] = dot[r];
+            }
+        }
+        e2 += (double)s;
+    }
+    const double tot = block_sum_d(e2, s_red);
+    if (threadIdx.x == 0) err_partial[(long long)b * gridDim.x + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kThreads)
+err_reduce_kernel(ClipState* __restrict__ st, int B, const double* __restrict__ err_partial, int n) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double v = 0.0;
+    for (int i = lane; i < n; i += 32) v += err_partial[(long long)b * n + i];
+    v = warp_sum_d(v);
+    if (lane == 0) st[b].err = (float)sqrt(v);
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+template <int KP>
+static cudaError_t run_gram(const float* A, long long a_stride, int rows, int B, const NmfWork& wk, float* G,
+                            const ClipState* st, cudaStream_t s) {
+    int P = ceil_div(rows, 256);
+    if (P > wk.gram_max_blocks) P = wk.gram_max_blocks;
+    if (P < 1) P = 1;
+    const int rpb = round_up(ceil_div(rows, P), 32);
+    P = ceil_div(rows, rpb);
+    AINMF_LAUNCH(gram_kernel<KP>, dim3(P, B), dim3(kThreads), 0, s, A, a_stride, rows, rpb, wk.gram_partial, G,
+                 wk.counters, st);
+    return cudaGetLastError();
+}
+
+template <int KP, int BM>
+static cudaError_t run_h_step(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    using Cfg = HStepCfg<KP, BM>;
+    cudaError_t e = cudaFuncSetAttribute(h_step_kernel<KP, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    auto kern = h_step_kernel<KP, BM>;
+    AINMF_LAUNCH(kern, dim3(ceil_div(p.T, BM), p.B), dim3(kThreads), Cfg::smem_bytes, s, p.Xt,
+                 p.x_stride, p.ldf, p.F, p.T, p.W, p.w_stride, wk.WtW, p.Ht, p.h_stride, wk.violH, p.state);
+    return cudaGetLastError();
+}
+
+template <int KP>
+static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    constexpr int LW = 8;
+    cudaError_t e;
+    // W half-step
+    if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
+    const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
+    const int S = ceil_div(p.T, fps);
+    AINMF_LAUNCH(xht_kernel<KP>, dim3(ceil_div(p.F, 128), S, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf,
+                 p.F, p.T, p.Ht, p.h_stride, fps, wk.xht_partial, p.state);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    {
+        const size_t smem = sizeof(float) * (size_t)KP * (KP + 4 * LW);
+        if ((e = cudaFuncSetAttribute(w_sweep_kernel<KP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        auto kern = w_sweep_kernel<KP, LW>;
+        AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(kThreads), smem, s, p.W, p.w_stride, p.F,
+                     wk.HHt, wk.xht_partial, S, wk.violW, p.state);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    // H half-step
+    if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
+    if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
+    else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s);
+    else e = run_h_step<KP, 128>(p, wk, s);
+    if (e != cudaSuccess) return e;
+    AINMF_LAUNCH(stop_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B, wk.violW,
+                 wk.nW, wk.violH, wk.nH, it, p.tol);
+    return cudaGetLastError();
+}
+
+cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    switch (p.KP) {
+        case 32: return iterate_impl<32>(p, wk, it, s);
+        case 64: return iterate_impl<64>(p, wk, it, s);
+        case 128: return iterate_impl<128>(p, wk, it, s);
+    }
+    return (cudaError_t)1;
+}
+
+template <int KP>
+static cudaError_t finalize_impl(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad,
+                                 long long bad_stride, cudaStream_t s) {
+    const int n = ceil_div(p.T, 16);
+    AINMF_LAUNCH(finalize_kernel<KP>, dim3(n, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf, p.F, p.T, p.W,
+                 p.w_stride, p.Ht, p.h_stride, bad, bad_stride, wk.err_partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    AINMF_LAUNCH(err_reduce_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B,
+                 wk.err_partial, n);
+    return cudaGetLastError();
+}
+
+cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
+                         cudaStream_t s) {
+    switch (p.KP) {
+        case 32: return finalize_impl<32>(p, wk, bad, bad_stride, s);
+        case 64: return finalize_impl<64>(p, wk, bad, bad_stride, s);
+        case 128: return finalize_impl<128>(p, wk, bad, bad_stride, s);
+    }
+    return (cudaError_t)1;
+}
+
+// Workspace layout for the iteration (all sizes in bytes, 256-aligned), see NmfWork in kernels.h.
+static size_t al256(size_t n) { return (n + 255) / 256 * 256; }
+
+void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
+    // h-step tile: the largest BM that still gives every SM two blocks
+    const long long want = 2LL * n_sm;
+    int bm = 128;
+    if ((long long)B * ceil_div(T, 128) < want) bm = 64;
+    if ((long long)B * ceil_div(T, 64) < want) bm = 32;
+    if (KP == 128 && bm == 128) bm = 64;                    // keeps two blocks per SM resident (smem)
+    wk->h_bm = bm;
+    wk->nH = ceil_div(T, bm);
+    wk->nW = ceil_div(F, kThreads / 8);
+    const int f_tiles = ceil_div(F, 128);
+    long long splits = want / ((long long)B * f_tiles);
+    if (splits < 1) splits = 1;
+    if (splits > ceil_div(T, 16)) splits = ceil_div(T, 16);
+    wk->xht_splits = (int)splits;
+    long long gb = want / B;
+    if (gb < 1) gb = 1;
+    if (gb > want) gb = want;
+    wk->gram_max_blocks = (int)gb;
+}
+
+size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
+    size_t n = 0;
+    n += al256(sizeof(float) * (size_t)B * KP * KP) * 2;                          // HHt, WtW
+    n += al256(sizeof(float) * (size_t)B * wk.gram_max_blocks * KP * KP);          // gram partials
+    n += al256(sizeof(unsigned) * (size_t)B);                                      // counters
+    n += al256(sizeof(float) * (size_t)B * (wk.xht_splits + 1) * F * KP);           // xht partials
+    n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
+    n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
+    return n;
+}
+
+void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) { char* r = p; p += al256(bytes); return r; };
+    wk->HHt = (float*)take(sizeof(float) * (size_t)B * KP * KP);
+    wk->WtW = (float*)take(sizeof(float) * (size_t)B * KP * KP);
+    wk->gram_partial = (float*)take(sizeof(float) * (size_t)B * wk->gram_max_blocks * KP * KP);
+    wk->counters = (unsigned*)take(sizeof(unsigned) * (size_t)B);
+    wk->xht_partial = (float*)take(sizeof(float) * (size_t)B * (wk->xht_splits + 1) * F * KP);
+    wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
+    wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);
+    wk->err_partial = (double*)take(sizeof(double) * (size_t)B * ceil_div(T, 16));
+}
+
+}  // namespace ainmf

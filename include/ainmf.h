@@ -1,0 +1,153 @@
+/*
+ * ainmf.h -- C ABI of libainmf.so: B200-native NMF spectrogram inpainting.
+ *
+ * The reference (conniemessi/Audio-Inpainting) has no FFI; its boundary for this path is the body of
+ *   NMFFairGapInpainter.restore / get_gap_mask        main4_NMF_gap.py:42-72 / :28-40
+ *   NMFFairInpainter.restore / get_mask_from_signal   main4_NMF_mask.py:47-77 / :28-45
+ *   SpectralInpainter.restore_with_nmf                main4_NMF.py:62-112
+ * i.e. normalised float32 waveform in -> restored float32 waveform out, through three third-party calls
+ * (scipy.signal.stft, sklearn.decomposition.NMF.fit_transform, scipy.signal.istft).  Each entry point below
+ * names the reference lines it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated;
+ *   - return value: 0 on success, negative ainmf_status otherwise; text via ainmf_last_error();
+ *   - no CPU fallback exists: without a CUDA device ainmf_create fails;
+ *   - layouts are the reference's: spectrogram-shaped outputs are (F, T) row-major exactly like the
+ *     arrays `signal.stft` returns and `NMF` consumes ("W" is (F, K), "H" is (K, T)), EXCEPT the *_tf
+ *     entry points, which use the library's internal frame-major [T][ldf] layout and avoid transposes.
+ */
+#ifndef AINMF_H
+#define AINMF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ainmf_context* ainmf_handle;
+
+enum ainmf_status {
+    AINMF_OK = 0,
+    AINMF_ERR_INVALID = -1,     /* bad argument (message says which) */
+    AINMF_ERR_CUDA = -2,        /* CUDA runtime error */
+    AINMF_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+    AINMF_ERR_WORKSPACE = -4,   /* workspace too small */
+    AINMF_ERR_ALL_BAD = -5,     /* every frame of a clip is flagged: mean of empty set (reference: NaN) */
+    AINMF_ERR_COMM = -6         /* NCCL error */
+};
+
+enum ainmf_solver {
+    AINMF_SOLVER_CD = 0,        /* sklearn solver='cd', beta_loss='frobenius' -- what the reference runs */
+    AINMF_SOLVER_MU = 1         /* multiplicative update, Frobenius (sklearn solver='mu') */
+};
+
+/* Parameters of one inpainting problem.  Defaults of the reference in brackets. */
+typedef struct ainmf_params {
+    int32_t batch;          /* B independent clips */
+    int64_t n_samples;      /* N samples per clip */
+    int32_t n_fft;          /* nperseg [1024 gap/mask, 512 part0]; power of two, 64..4096 */
+    int32_t hop;            /* n_fft - noverlap [256 / 128]; must divide n_fft, n_fft/hop <= 8 */
+    int32_t rank;           /* n_components K [40]; 1..128 */
+    int32_t max_iter;       /* [200] */
+    float tol;              /* [1e-4] */
+    int32_t solver;         /* ainmf_solver [CD] */
+    uint32_t seed;          /* random_state [42 gap/mask, 0 part0]; used when W0/H0 are null */
+    float threshold;        /* |x| < threshold marks a silent sample [1e-4 gap, 0.01 mask] */
+    int32_t frac_num;       /* column is bad iff silent fraction > frac_num/frac_den [9/10 gap, 4/5 mask] */
+    int32_t frac_den;
+    int32_t col_start;      /* >= 0: bad frames are [col_start, col_end) and the fill is the mean of the */
+    int32_t col_end;        /*       frames before col_start (main4_NMF.py:74-81); < 0: detect from x  */
+    int32_t n_outer;        /* number of refits, each followed by bad frames <- W.H [1; 50 in main4_NMF.py:86-90] */
+} ainmf_params;
+
+/* ---- handle ------------------------------------------------------------------------------------------ */
+int ainmf_create(ainmf_handle* out, int device);
+int ainmf_destroy(ainmf_handle h);
+const char* ainmf_last_error(ainmf_handle h);   /* h may be NULL: error of the last failed ainmf_create */
+const char* ainmf_version(void);
+void ainmf_params_default(ainmf_params* p);     /* the constants of main4_NMF_gap.py */
+
+/* ---- geometry ---------------------------------------------------------------------------------------- */
+/* Frame count T, bins F = n_fft/2+1 and internal leading dimension ldf of scipy.signal.stft(x, nperseg=n_fft,
+ * noverlap=n_fft-hop) with its defaults boundary='zeros', padded=True ($SP/scipy/signal/_spectral_py.py:2240-2247). */
+int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf);
+int32_t ainmf_padded_rank(int32_t rank);        /* 32, 64 or 128 */
+
+/* ---- stage entry points (device buffers) --------------------------------------------------------------- */
+/* signal.stft + np.abs (main4_NMF_gap.py:47-48).  mag_ft [B][F][T] float, Z_ft [B][F][T] complex64 (re,im). Either
+ * may be NULL.  The window is periodic Hann, scipy's default. */
+int ainmf_stft(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, int32_t n_fft, int32_t hop,
+               float* mag_ft, float* Z_ft, void* stream);
+
+/* get_gap_mask / get_mask_from_signal (main4_NMF_gap.py:28-40, main4_NMF_mask.py:28-45).
+ * bad [B][n_frames] uint8 flags; bad_idx [B][n_frames] int32 ascending indices (first n_bad[b] valid); n_bad [B]. */
+int ainmf_gap_mask(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, int32_t hop, int32_t n_frames,
+                   float threshold, int32_t frac_num, int32_t frac_den, uint8_t* bad, int32_t* bad_idx,
+                   int32_t* n_bad, void* stream);
+
+/* NMF(n_components=K, init='custom'|'random', max_iter, tol).fit_transform(X) (main4_NMF_gap.py:62-64;
+ * $SP/sklearn/decomposition/_nmf.py:399-518, _cdnmf_fast.pyx:8-38).  X_ft [B][F][T] non-negative.
+ * W0 [B][F][K], H0 [B][K][T]: initial factors, or both NULL to draw them from `seed` exactly as
+ * sklearn's init='random' does.  Outputs W [B][F][K], H [B][K][T], err [B] (reconstruction_err_),
+ * n_iter [B] (n_iter_); any output may be NULL. */
+int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, int32_t T, int32_t rank,
+                  int32_t max_iter, float tol, int32_t solver, uint32_t seed, const float* W0, const float* H0,
+                  float* W, float* H, float* err, int32_t* n_iter, void* stream);
+
+/* signal.istft + [:N] (main4_NMF_gap.py:71-72).  Z_ft [B][F][T] complex64; y [B][N]. */
+int ainmf_istft(ainmf_handle h, const float* Z_ft, int32_t batch, int32_t T, int32_t n_fft, int32_t hop,
+                int64_t n_samples, float* y, void* stream);
+
+/* ---- the whole path --------------------------------------------------------------------------------- */
+/* Bytes of device workspace ainmf_inpaint needs for `p` (0 on invalid parameters). */
+size_t ainmf_workspace_bytes(ainmf_handle h, const ainmf_params* p);
+
+/* restore() of main4_NMF_gap.py:42-72 / main4_NMF_mask.py:47-77, or restore_with_nmf() of main4_NMF.py:62-95
+ * when p->col_start >= 0 (without _blend_boundaries, which needs the ground truth).
+ *   x [B][N] normalised corrupted waveform -> y [B][N] restored waveform (y = x for clips with no bad frame).
+ * Optional outputs (NULL to skip): bad_idx [B][T] int32, n_bad [B], W [B][F][K], H [B][K][T], err [B], n_iter [B]
+ * (of the last refit).  W0/H0 as in ainmf_nmf_fit.  Synchronises `stream` only to poll the stop flags
+ * (every few iterations) when p->tol > 0. */
+int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const float* W0, const float* H0, float* y,
+                  int32_t* bad_idx, int32_t* n_bad, float* W, float* H, float* err, int32_t* n_iter,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same with HOST buffers: stages x through pinned memory, runs ainmf_inpaint in clip chunks sized to
+ * `max_device_bytes` (0: 80 % of free memory), copies y (and the optional outputs) back, and synchronises.
+ * This is the call bench.py times for the end-to-end figure. */
+int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, int32_t* n_bad_host,
+                       float* err_host, int32_t* n_iter_host, size_t max_device_bytes);
+
+/* ---- front/back end of the scripts ------------------------------------------------------ */
+/* load_damaged_data (main4_NMF_gap.py:21-24): int16 [B][N][channels] -> mono mean -> float32 -> x / max|x| (true
+ * division).  peak [B] optional output. */
+int ainmf_load_pcm16(ainmf_handle h, const int16_t* pcm, int32_t batch, int64_t n_samples, int32_t channels, float* x,
+                     float* peak, void* stream);
+/* save_result (main4_NMF_gap.py:76-77): clip to [-1,1], * 32767, truncate toward zero. */
+int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pcm, void* stream);
+
+/* ---- time-frame sharding of one long signal ------------------------------------------------- */
+/* Join `nranks` handles (one per GPU / process) into a group.  unique_id is the 128-byte NCCL id produced by
+ * ainmf_comm_unique_id on rank 0 and distributed by the caller (torch.distributed broadcast). */
+int ainmf_comm_unique_id(uint8_t id_out[128]);
+int ainmf_comm_init(ainmf_handle h, const uint8_t unique_id[128], int32_t rank, int32_t nranks);
+/* Frames [t_begin, t_end) of a T-frame signal owned by `rank`, and the sample range of x that rank needs
+ * (its frames' support plus the mask/OLA halo), clipped to [0, N). */
+int ainmf_shard_plan(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t rank, int32_t nranks, int32_t* t_begin,
+                     int32_t* t_end, int64_t* x_begin, int64_t* x_end, int64_t* y_begin, int64_t* y_end);
+size_t ainmf_sharded_workspace_bytes(ainmf_handle h, const ainmf_params* p);
+/* One rank's part of the whole path on a signal split by time frames: x_local = x[x_begin:x_end) of the
+ * plan, y_local = y[y_begin:y_end).  W is replicated, H/V are sliced; per iteration the F*K + K*K partial sums of
+ * the W half-step (and one violation scalar) are all-reduced over NVLink.  batch must be 1. */
+int ainmf_inpaint_sharded(ainmf_handle h, const ainmf_params* p, const float* x_local, float* y_local, int32_t* n_bad,
+                          float* W, float* H_local, float* err, int32_t* n_iter, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AINMF_H */
