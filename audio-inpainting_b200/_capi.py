@@ -12,7 +12,7 @@ EXPORTS = [
     "ainmf_stft_geometry", "ainmf_padded_rank", "ainmf_stft", "ainmf_gap_mask", "ainmf_nmf_fit", "ainmf_istft",
     "ainmf_workspace_bytes", "ainmf_inpaint", "ainmf_inpaint_host", "ainmf_load_pcm16", "ainmf_store_pcm16",
     "ainmf_comm_unique_id", "ainmf_comm_init", "ainmf_shard_plan", "ainmf_sharded_workspace_bytes",
-    "ainmf_inpaint_sharded",
+    "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile",
 ]
 
 
@@ -46,6 +46,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "ainmf_inpaint_host": (C.c_int, [vp, P(Params), vp, vp, vp, vp, vp, sz]),
         "ainmf_load_pcm16": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
         "ainmf_store_pcm16": (C.c_int, [vp, vp, i64, vp, vp]),
+        "ainmf_launch_count": (C.c_ulonglong, []),
+        "ainmf_profile": (C.c_int, [vp, i32, vp, vp]),
         "ainmf_comm_unique_id": (C.c_int, [vp]),
         "ainmf_comm_init": (C.c_int, [vp, vp, i32, i32]),
         "ainmf_shard_plan": (C.c_int, [i64, i32, i32, i32, i32, P(i32), P(i32), P(i64), P(i64), P(i64), P(i64)]),

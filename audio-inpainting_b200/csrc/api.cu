@@ -680,6 +680,20 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     return AINMF_OK;
 }
 
+unsigned long long ainmf_launch_count(void) { return ainmf::g_launch_count; }
+
+int ainmf_profile(ainmf_handle h, int32_t enable, double* ms_out, int64_t* counts_out) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (ms_out && counts_out) {
+        double ms[PROF_KINDS];
+        long long cn[PROF_KINDS];
+        prof_collect(ms, cn);
+        for (int i = 0; i < PROF_KINDS; ++i) { ms_out[i] = ms[i]; counts_out[i] = cn[i]; }
+    }
+    prof_enable(enable != 0);
+    return AINMF_OK;
+}
+
 int ainmf_load_pcm16(ainmf_handle h, const int16_t* pcm, int32_t batch, int64_t n_samples, int32_t channels, float* x,
                      float* peak, void* stream) {
     if (!h) return AINMF_ERR_INVALID;

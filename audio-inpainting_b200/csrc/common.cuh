@@ -14,7 +14,9 @@
 #include "emu/cuda_emu.h"
 #else
 #include <cuda_runtime.h>
-#define AINMF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+namespace ainmf { extern unsigned long long g_launch_count; }
+#define AINMF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (++ainmf::g_launch_count, kernel<<<grid, block, smem, stream>>>(__VA_ARGS__))
 #define AINMF_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #endif
 

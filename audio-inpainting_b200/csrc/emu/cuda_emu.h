@@ -165,6 +165,12 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef void* cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
@@ -214,5 +220,6 @@ inline unsigned char* dyn_smem_ptr() {
 }
 }  // namespace emu
 
-#define AINMF_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+namespace ainmf { extern unsigned long long g_launch_count; }
+#define AINMF_LAUNCH(kernel, grid, block, smem, stream, ...) (++ainmf::g_launch_count, emu::launch(kernel, grid, block, smem, __VA_ARGS__))
 #define AINMF_DYN_SMEM(name) unsigned char* name = emu::dyn_smem_ptr()

@@ -109,6 +109,14 @@ cudaError_t launch_export_state(const ClipState* st, int B, int* n_bad, int* n_i
 // state for a fit on a caller-provided X (no imputation stage): done=0, n_iter=0
 cudaError_t launch_reset_state(ClipState* st, int B, cudaStream_t s);
 
+// ---- profiling (CUDA events around the kernels of the iteration; off by default) -----------------------
+enum ProfKind { PROF_GRAM_H = 0, PROF_XHT, PROF_W_SWEEP, PROF_GRAM_W, PROF_H_STEP, PROF_STOP, PROF_KINDS };
+void prof_enable(bool on);
+void prof_begin(int kind, cudaStream_t s);
+void prof_end(int kind, cudaStream_t s);
+// synchronises the recorded events, adds the elapsed milliseconds / launch counts per kind, then resets
+void prof_collect(double* ms /*[PROF_KINDS]*/, long long* counts /*[PROF_KINDS]*/);
+
 // ---- nmf_cd.cu ----------------------------------------------------------------------------------
 struct NmfProblem {
     int B, T, F, ldf, KP;

@@ -5,7 +5,7 @@
 //     g[i]   = |x[i]| < float32(threshold)
 //     column c is bad  <=>  mean(g[ws:we]) > frac,  ws = max(0, c*hop - hop//2), we = min(N, c*hop + hop//2)
 // mean(bool) = cnt/len exactly and cnt/len > num/den <=> den*cnt > num*len (integers; verified
-// exhaustively in tests/test_oracle.py).  An empty window (numpy: mean of empty = nan) is not bad.
+// exhaustively by the CPU test-suite).  An empty window (numpy: mean of empty = nan) is not bad.
 #include "kernels.h"
 
 namespace ainmf {

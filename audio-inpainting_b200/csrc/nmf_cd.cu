@@ -13,7 +13,51 @@
 #include "kernels.h"
 #include "nmf_cd.cuh"
 
+#include <vector>
+
 namespace ainmf {
+
+unsigned long long g_launch_count = 0;
+
+// ---- profiling --------------------------------------------------------------------------------------------
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t g_prof_open[PROF_KINDS];
+cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+void prof_enable(bool on) { g_prof_on = on; }
+void prof_begin(int kind, cudaStream_t s) {
+    if (!g_prof_on) return;
+    g_prof_open[kind] = prof_event();
+    cudaEventRecord(g_prof_open[kind], s);
+}
+void prof_end(int kind, cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, s);
+    g_prof_recs.push_back({kind, g_prof_open[kind], e});
+}
+void prof_collect(double* ms, long long* counts) {
+    for (int i = 0; i < PROF_KINDS; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (const ProfRec& r : g_prof_recs) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.kind] += (double)t;
+        counts[r.kind] += 1;
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+}
 
 // =====================================================================================================
 // gram: G[b] = A[b]^T A[b] for A [rows][KP]; grid = (P, B); partials then last-block reduce.
@@ -509,29 +553,42 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     constexpr int LW = 8;
     cudaError_t e;
     // W half-step
+    prof_begin(PROF_GRAM_H, s);
     if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
+    prof_end(PROF_GRAM_H, s);
     const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
     const int S = ceil_div(p.T, fps);
+    prof_begin(PROF_XHT, s);
     AINMF_LAUNCH(xht_kernel<KP>, dim3(ceil_div(p.F, 128), S, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf,
                  p.F, p.T, p.Ht, p.h_stride, fps, wk.xht_partial, p.state);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    prof_end(PROF_XHT, s);
     {
         const size_t smem = sizeof(float) * (size_t)KP * (KP + 4 * LW);
         if ((e = cudaFuncSetAttribute(w_sweep_kernel<KP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         auto kern = w_sweep_kernel<KP, LW>;
+        prof_begin(PROF_W_SWEEP, s);
         AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(kThreads), smem, s, p.W, p.w_stride, p.F,
                      wk.HHt, wk.xht_partial, S, wk.violW, p.state);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        prof_end(PROF_W_SWEEP, s);
     }
     // H half-step
+    prof_begin(PROF_GRAM_W, s);
     if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
+    prof_end(PROF_GRAM_W, s);
+    prof_begin(PROF_H_STEP, s);
     if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
     else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s);
     else e = run_h_step<KP, 128>(p, wk, s);
     if (e != cudaSuccess) return e;
+    prof_end(PROF_H_STEP, s);
+    prof_begin(PROF_STOP, s);
     AINMF_LAUNCH(stop_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B, wk.violW,
                  wk.nW, wk.violH, wk.nH, it, p.tol);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    prof_end(PROF_STOP, s);
+    return e;
 }
 
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {

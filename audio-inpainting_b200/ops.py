@@ -1,0 +1,202 @@
+"""PyTorch custom ops `torch.ops.ainmf.*` over the C ABI of libainmf.so.
+
+CUDA tensors only (no CPU kernels are registered: calling an op with CPU tensors raises NotImplementedError from
+the dispatcher).  Work is enqueued on the current CUDA stream of the tensors' device; no autograd.
+
+Shapes follow the reference's arrays: spectrogram-like tensors are (B, F, T) as returned by
+`scipy.signal.stft` / consumed by `sklearn.decomposition.NMF` (main4_NMF_gap.py:47-64).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi, _lib
+
+_LIBRARY = torch.library.Library("ainmf", "DEF")
+_LIBRARY.define("stft(Tensor x, int n_fft, int hop) -> (Tensor, Tensor)")
+_LIBRARY.define("gap_mask(Tensor x, int hop, int n_frames, float threshold, int frac_num, int frac_den) "
+                "-> (Tensor, Tensor, Tensor)")
+_LIBRARY.define("nmf_fit(Tensor X, int rank, int max_iter, float tol, int seed, Tensor? W0, Tensor? H0) "
+                "-> (Tensor, Tensor, Tensor, Tensor)")
+_LIBRARY.define("istft(Tensor Z, int n_fft, int hop, int length) -> Tensor")
+_LIBRARY.define("nmf_inpaint(Tensor x, int n_fft, int hop, int rank, int max_iter, float tol, int seed, "
+                "float threshold, int frac_num, int frac_den, int col_start, int col_end, int n_outer, "
+                "Tensor? W0, Tensor? H0) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+_LIBRARY.define("load_pcm16(Tensor pcm) -> (Tensor, Tensor)")
+_LIBRARY.define("store_pcm16(Tensor y) -> Tensor")
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("ainmf ops take CUDA tensors only (there is no CPU implementation)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev: int) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stft(x, n_fft, hop):
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        T, F, _ = _capi.stft_geometry(L, N, n_fft, hop)
+        mag = torch.empty((B, F, T), dtype=torch.float32, device=x.device)
+        Z = torch.empty((B, F, T), dtype=torch.complex64, device=x.device)
+        _lib.check(L.ainmf_stft(_lib.handle(dev), _p(x), B, N, n_fft, hop, _p(mag), _p(Z), _stream(dev)), dev)
+    return mag, Z
+
+
+def _gap_mask(x, hop, n_frames, threshold, frac_num, frac_den):
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        bad = torch.empty((B, n_frames), dtype=torch.uint8, device=x.device)
+        idx = torch.full((B, n_frames), -1, dtype=torch.int32, device=x.device)
+        nb = torch.empty((B,), dtype=torch.int32, device=x.device)
+        _lib.check(L.ainmf_gap_mask(_lib.handle(dev), _p(x), B, N, hop, n_frames, threshold, frac_num, frac_den,
+                                    _p(bad), _p(idx), _p(nb), _stream(dev)), dev)
+    return bad, idx, nb
+
+
+def _nmf_fit(X, rank, max_iter, tol, seed, W0, H0):
+    X = _f32(X, "X")
+    if X.dim() != 3:
+        raise RuntimeError("X must be [B, F, T]")
+    dev = _dev(X)
+    B, F, T = X.shape
+    if (W0 is None) != (H0 is None):
+        raise RuntimeError("W0 and H0 must be given together")
+    if W0 is not None:
+        W0 = _f32(W0, "W0").expand(B, F, rank).contiguous()
+        H0 = _f32(H0, "H0").expand(B, rank, T).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        W = torch.empty((B, F, rank), dtype=torch.float32, device=X.device)
+        H = torch.empty((B, rank, T), dtype=torch.float32, device=X.device)
+        err = torch.empty((B,), dtype=torch.float32, device=X.device)
+        nit = torch.empty((B,), dtype=torch.int32, device=X.device)
+        _lib.check(L.ainmf_nmf_fit(_lib.handle(dev), _p(X), B, F, T, rank, max_iter, tol, _capi.SOLVER_CD,
+                                   seed & 0xFFFFFFFF, _p(W0), _p(H0), _p(W), _p(H), _p(err), _p(nit),
+                                   _stream(dev)), dev)
+    return W, H, err, nit
+
+
+def _istft(Z, n_fft, hop, length):
+    if Z.dtype != torch.complex64 or Z.dim() != 3:
+        raise RuntimeError("Z must be complex64 [B, F, T]")
+    Z = Z.contiguous()
+    dev = _dev(Z)
+    B, F, T = Z.shape
+    if F != n_fft // 2 + 1:
+        raise RuntimeError(f"Z has {F} bins, n_fft={n_fft} needs {n_fft // 2 + 1}")
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        y = torch.empty((B, length), dtype=torch.float32, device=Z.device)
+        _lib.check(L.ainmf_istft(_lib.handle(dev), _p(Z), B, T, n_fft, hop, length, _p(y), _stream(dev)), dev)
+    return y
+
+
+_workspaces: dict[int, torch.Tensor] = {}
+
+
+def _workspace(dev: int, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces.pop(dev, None)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=torch.device("cuda", dev))
+        _workspaces[dev] = ws
+    return ws
+
+
+def _nmf_inpaint(x, n_fft, hop, rank, max_iter, tol, seed, threshold, frac_num, frac_den, col_start, col_end,
+                 n_outer, W0, H0):
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        h = _lib.handle(dev)
+        p = _capi.default_params(L, batch=B, n_samples=N, n_fft=n_fft, hop=hop, rank=rank, max_iter=max_iter, tol=tol,
+                                 seed=seed & 0xFFFFFFFF, threshold=threshold, frac_num=frac_num, frac_den=frac_den,
+                                 col_start=col_start, col_end=col_end, n_outer=n_outer)
+        nbytes = L.ainmf_workspace_bytes(h, C.byref(p))
+        if nbytes == 0:
+            _lib.check(_capi.ERR_INVALID, dev)
+        T, F, _ = _capi.stft_geometry(L, N, n_fft, hop)
+        if (W0 is None) != (H0 is None):
+            raise RuntimeError("W0 and H0 must be given together")
+        if W0 is not None:
+            W0 = _f32(W0, "W0").expand(B, F, rank).contiguous()
+            H0 = _f32(H0, "H0").expand(B, rank, T).contiguous()
+        ws = _workspace(dev, nbytes)
+        y = torch.empty((B, N), dtype=torch.float32, device=x.device)
+        idx = torch.full((B, T), -1, dtype=torch.int32, device=x.device)
+        nb = torch.zeros((B,), dtype=torch.int32, device=x.device)
+        W = torch.zeros((B, F, rank), dtype=torch.float32, device=x.device)
+        H = torch.zeros((B, rank, T), dtype=torch.float32, device=x.device)
+        err = torch.zeros((B,), dtype=torch.float32, device=x.device)
+        nit = torch.zeros((B,), dtype=torch.int32, device=x.device)
+        _lib.check(L.ainmf_inpaint(h, C.byref(p), _p(x), _p(W0), _p(H0), _p(y), _p(idx), _p(nb), _p(W), _p(H),
+                                   _p(err), _p(nit), _p(ws), ws.numel(), _stream(dev)), dev)
+    return y, idx, nb, W, H, err, nit
+
+
+def _load_pcm16(pcm):
+    if pcm.dtype != torch.int16 or pcm.dim() not in (2, 3):
+        raise RuntimeError("pcm must be int16 [B, N] or [B, N, C]")
+    pcm = pcm.contiguous()
+    dev = _dev(pcm)
+    B, N = pcm.shape[:2]
+    ch = pcm.shape[2] if pcm.dim() == 3 else 1
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        x = torch.empty((B, N), dtype=torch.float32, device=pcm.device)
+        peak = torch.empty((B,), dtype=torch.float32, device=pcm.device)
+        _lib.check(L.ainmf_load_pcm16(_lib.handle(dev), _p(pcm), B, N, ch, _p(x), _p(peak), _stream(dev)), dev)
+    return x, peak
+
+
+def _store_pcm16(y):
+    y = _f32(y, "y")
+    dev = _dev(y)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = torch.empty(y.shape, dtype=torch.int16, device=y.device)
+        _lib.check(L.ainmf_store_pcm16(_lib.handle(dev), _p(y), y.numel(), _p(out), _stream(dev)), dev)
+    return out
+
+
+for _name, _fn in (("stft", _stft), ("gap_mask", _gap_mask), ("nmf_fit", _nmf_fit), ("istft", _istft),
+                   ("nmf_inpaint", _nmf_inpaint), ("load_pcm16", _load_pcm16), ("store_pcm16", _store_pcm16)):
+    _LIBRARY.impl(_name, _fn, "CUDA")
+
+stft = torch.ops.ainmf.stft
+gap_mask = torch.ops.ainmf.gap_mask
+nmf_fit = torch.ops.ainmf.nmf_fit
+istft = torch.ops.ainmf.istft
+nmf_inpaint = torch.ops.ainmf.nmf_inpaint
+load_pcm16 = torch.ops.ainmf.load_pcm16
+store_pcm16 = torch.ops.ainmf.store_pcm16

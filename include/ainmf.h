@@ -130,6 +130,14 @@ int ainmf_load_pcm16(ainmf_handle h, const int16_t* pcm, int32_t batch, int64_t 
 /* save_result (main4_NMF_gap.py:76-77): clip to [-1,1], * 32767, truncate toward zero. */
 int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pcm, void* stream);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------ */
+/* Number of kernels this library has launched in this process (monotonic). */
+unsigned long long ainmf_launch_count(void);
+/* Kernel timing of the NMF iteration with CUDA events on the launching stream.  Reads (and clears) the time
+ * accumulated since the last call into ms_out[6] / counts_out[6] -- order: gram(Ht), X.Ht partials, W sweep,
+ * gram(W), fused X^T.W + H sweep, stop rule -- then switches recording on or off.  ms_out/counts_out may be NULL. */
+int ainmf_profile(ainmf_handle h, int32_t enable, double* ms_out, int64_t* counts_out);
+
 /* ---- time-frame sharding of one long signal ------------------------------------------------- */
 /* Join `nranks` handles (one per GPU / process) into a group.  unique_id is the 128-byte NCCL id produced by
  * ainmf_comm_unique_id on rank 0 and distributed by the caller (torch.distributed broadcast). */

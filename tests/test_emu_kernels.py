@@ -1,0 +1,108 @@
+"""Kernel-logic tests without a GPU: the CUDA sources compiled for the host against csrc/emu/cuda_emu.h
+(tests/emu_harness.py) and driven through the same C ABI, compared with the oracle on small seeded inputs.
+This checks indexing, tiling, reductions and the host-side orchestration; the real parity tests are the
+`-m gpu` ones, which run the sm_100a build."""
+import numpy as np
+import pytest
+from scipy import signal
+
+import emu_harness as E
+from oracle import libcalls, restate
+
+SR = 8000
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300))
+
+
+@pytest.mark.parametrize("N,n_fft,hop", [(3000, 128, 32), (1111, 64, 16), (2500, 256, 64)])
+def test_emu_stft_istft(N, n_fft, hop):
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((2, N)).astype(np.float32)
+    mag, Z = E.stft(x, n_fft, hop)
+    for b in range(2):
+        _, _, Zs = signal.stft(x[b], SR, nperseg=n_fft, noverlap=n_fft - hop)
+        assert Z[b].shape == Zs.shape
+        assert rel_l2(Z[b], Zs) < 1e-6 and rel_l2(mag[b], np.abs(Zs)) < 1e-6
+    _, _, Zs = signal.stft(x[0], SR, nperseg=n_fft, noverlap=n_fft - hop)
+    Zs = (Zs * (1 + 0.2 * rng.standard_normal(Zs.shape))).astype(np.complex64)
+    _, ys = signal.istft(Zs, SR, nperseg=n_fft, noverlap=n_fft - hop)
+    y = E.istft(Zs, n_fft, hop, N)
+    assert rel_l2(y[0], ys[:N]) < 1e-6
+
+
+@pytest.mark.parametrize("thr,num,den,frac", [(1e-4, 9, 10, 0.9), (0.01, 4, 5, 0.8)])
+def test_emu_mask_bit_exact(thr, num, den, frac):
+    rng = np.random.default_rng(4)
+    for N, n_fft, hop in [(5000, 128, 32), (3333, 256, 64), (900, 64, 16)]:
+        x = rng.standard_normal((2, N)).astype(np.float32) * 0.1
+        for b in range(2):
+            for _ in range(8):
+                a = rng.integers(0, N)
+                x[b, a:a + rng.integers(1, 5 * hop)] = 0
+            x[b, rng.integers(0, N, 20)] = np.float32(thr)
+        T, _ = restate.stft_geometry(N, n_fft, hop)
+        bad, idx, nb = E.gap_mask(x, hop, T, thr, num, den)
+        for b in range(2):
+            want = libcalls.column_mask(x[b], T, hop, thr, frac)
+            assert nb[b] == len(want) and np.array_equal(idx[b, :nb[b]], want)
+
+
+@pytest.mark.parametrize("F,T,K,iters", [(65, 95, 8, 4), (33, 70, 40, 3), (130, 40, 100, 2)])
+def test_emu_nmf_fit(F, T, K, iters):
+    rng = np.random.default_rng(F)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    W, H, err, nit = E.nmf_fit(X, K, max_iter=iters, tol=0.0, seed=42)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, seed=42, max_iter=iters, tol=0.0)
+    assert nit[0] == no
+    assert abs(err[0] - eo) < 1e-5 * eo
+    assert rel_l2(W[0], Wo) < 1e-4 and rel_l2(H[0], Ho) < 1e-4
+
+
+def test_emu_whole_path_and_edge_cases():
+    rng = np.random.default_rng(2)
+    N, n_fft, hop, K = 6000, 128, 32, 8
+    t = np.arange(N) / SR
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.3 * np.sin(2 * np.pi * 1230 * t) + 0.05 * rng.standard_normal(N)).astype(np.float32)
+    x[2500:3300] = 0
+    x /= np.abs(x).max()
+    x2 = x.copy()
+    x2[2500:3300] = x[1000:1800]                      # a clip with nothing to restore
+    r = E.inpaint(np.stack([x, x2]), n_fft=n_fft, hop=hop, rank=K, max_iter=5, tol=1e-4, seed=42)
+    y, st = libcalls.restore_columns(x, SR, n_fft=n_fft, hop=hop, K=K, seed=42, max_iter=5, return_all=True)
+    assert np.array_equal(r["bad_idx"][0][:r["n_bad"][0]], st["bad"])
+    assert r["n_iter"][0] == st["n_iter"] and abs(r["err"][0] - st["err"]) < 1e-5 * st["err"]
+    assert libcalls.snr_db(y, r["y"][0]) > 90 and libcalls.snr_db(y[2500:3300], r["y"][0][2500:3300]) > 70
+    assert r["n_bad"][1] == 0 and np.array_equal(r["y"][1], x2)      # input returned untouched
+    with pytest.raises(E.capi.AinmfError) as e:
+        E.inpaint(np.zeros(6016, np.float32), n_fft=n_fft, hop=hop, rank=K, max_iter=2)   # 6016 = 188*hop: no empty window
+    assert e.value.code == E.capi.ERR_ALL_BAD
+
+
+def test_emu_part0_variant():
+    """col_start/col_end + n_outer (main4_NMF.py:74-90) against the library-call oracle."""
+    rng = np.random.default_rng(6)
+    sr, N, n_fft, hop, K = 8000, 1600, 128, 32, 8
+    t = np.arange(N) / sr
+    raw = (0.6 * np.sin(2 * np.pi * 300 * t) + 0.2 * np.sin(2 * np.pi * 900 * t) + 0.02 * rng.standard_normal(N)).astype(np.float32)
+    cor, gs, ge = libcalls.part0_apply_mask(raw, 0.2)
+    yo, so = libcalls.part0_restore(raw, cor, sr, gs, ge, n_fft=n_fft, hop=hop, K=K, n_outer=3, seed=0,
+                                    max_iter=25, return_all=True)
+    cs, ce = so["cols"]
+    r = E.inpaint(cor, n_fft=n_fft, hop=hop, rank=K, max_iter=25, tol=1e-4, seed=0, col_start=cs, col_end=ce, n_outer=3)
+    assert abs(int(r["n_iter"][0]) - so["n_iters"][-1]) <= 1
+    assert libcalls.snr_db(so["pre_blend"], r["y"][0]) > 60
+
+
+def test_emu_invalid_arguments():
+    x = np.zeros(4000, np.float32)
+    for kw in (dict(n_fft=100, hop=25), dict(n_fft=128, hop=48), dict(rank=0), dict(rank=129), dict(max_iter=0),
+               dict(n_fft=8192, hop=2048), dict(col_start=0, col_end=3), dict(n_outer=0), dict(solver=1)):
+        p = dict(n_fft=128, hop=32, rank=8, max_iter=2)
+        p.update(kw)
+        with pytest.raises(E.capi.AinmfError) as e:
+            E.inpaint(x, **p)
+        assert e.value.code == E.capi.ERR_INVALID, kw
+    with pytest.raises(E.capi.AinmfError):
+        E.stft(np.zeros(50, np.float32), 128, 32)

@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path (through torch.ops.ainmf -> C ABI -> sm_100a kernels) against the oracle.
+
+Tolerances are north_star's: masks / indices bit-exact; |Z| rel-L2 <= 1e-5; objective rel <= 1e-4;
+restored-waveform SNR vs the reference output >= 60 dB (in-gap SNR is reported and gated at >= 40 dB, the
+whole-wave figure being dominated by untouched frames).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import libcalls, restate  # noqa: E402
+
+SR = 44100
+
+
+def rel_l2(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests (no CPU fallback exists)")
+    import ainmf
+    return ainmf.ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- K1 / K5 --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,n_fft,hop", [(2205, 512, 128), (441000, 1024, 256), (441000, 2048, 512),
+                                         (5000, 256, 64), (4096, 64, 16), (100000, 4096, 1024), (1024, 1024, 256)])
+def test_stft_matches_scipy(ops, N, n_fft, hop):
+    from scipy import signal
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((2, N)).astype(np.float32)
+    mag, Z = ops.stft(dev(x), n_fft, hop)
+    for b in range(2):
+        _, _, Zs = signal.stft(x[b], SR, nperseg=n_fft, noverlap=n_fft - hop)
+        assert tuple(Z[b].shape) == Zs.shape
+        assert rel_l2(mag[b].cpu().numpy(), np.abs(Zs)) <= 1e-5          # north_star: 1e-5 relative L2
+        assert rel_l2(Z[b].cpu().numpy(), Zs) <= 1e-5
+
+
+@pytest.mark.parametrize("N,n_fft,hop", [(2205, 512, 128), (441000, 1024, 256), (30000, 2048, 512), (4096, 64, 16)])
+def test_istft_matches_scipy(ops, N, n_fft, hop):
+    from scipy import signal
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(N).astype(np.float32)
+    _, _, Z = signal.stft(x, SR, nperseg=n_fft, noverlap=n_fft - hop)
+    Z = (Z * (1 + 0.3 * rng.standard_normal(Z.shape))).astype(np.complex64)
+    _, ys = signal.istft(Z, SR, nperseg=n_fft, noverlap=n_fft - hop)
+    y = ops.istft(dev(Z[None]), n_fft, hop, N)[0].cpu().numpy()
+    assert rel_l2(y, ys[:N]) <= 1e-5
+
+
+def test_stft_istft_round_trip_full_size(ops):
+    """Size-independent property at BASELINE sizes: istft(stft(x)) == x (NOLA holds for Hann, 75 % overlap)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((8, 441000), generator=g, device="cuda")
+    for n_fft, hop in ((1024, 256), (2048, 512)):
+        _, Z = ops.stft(x, n_fft, hop)
+        y = ops.istft(Z, n_fft, hop, x.shape[1])
+        err = (y - x).norm() / x.norm()
+        assert float(err) < 1e-5
+
+
+def test_stft_is_linear(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randn((1, 50000), generator=g, device="cuda")
+    b = torch.randn((1, 50000), generator=g, device="cuda")
+    _, Za = ops.stft(a, 1024, 256)
+    _, Zb = ops.stft(b, 1024, 256)
+    _, Zc = ops.stft(2 * a - 3 * b, 1024, 256)
+    assert float((Zc - (2 * Za - 3 * Zb)).abs().max() / Zc.abs().max()) < 1e-5
+
+
+# ---- K2 (bit-exact) --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr,num,den,frac", [(1e-4, 9, 10, 0.9), (0.01, 4, 5, 0.8)])
+def test_mask_bit_exact_random(ops, thr, num, den, frac):
+    rng = np.random.default_rng(3)
+    for N, n_fft, hop in [(20000, 1024, 256), (12345, 512, 128), (441000, 2048, 512), (700, 256, 64), (441000, 1024, 256)]:
+        x = rng.standard_normal(N).astype(np.float32) * 0.1
+        for _ in range(20):
+            a = rng.integers(0, N)
+            x[a:a + rng.integers(1, 4 * hop)] = 0
+        x[rng.integers(0, N, 50)] = np.float32(thr)
+        x[rng.integers(0, N, 50)] = np.nextafter(np.float32(thr), np.float32(0))
+        T, _ = restate.stft_geometry(N, n_fft, hop)
+        want = libcalls.column_mask(x, T, hop, thr, frac)
+        bad, idx, nb = ops.gap_mask(dev(x[None]), hop, T, thr, num, den)
+        n = int(nb[0])
+        assert n == len(want)
+        assert np.array_equal(idx[0, :n].cpu().numpy().astype(np.int64), want)
+        assert np.array_equal(np.nonzero(bad[0].cpu().numpy())[0], want)
+
+
+def test_mask_golden_c2_c3(ops, golden):
+    x2 = libcalls.load_normalised(golden.gap_input_i16())
+    _, idx, nb = ops.gap_mask(dev(x2[None]), 256, 1724, 1e-4, 9, 10)
+    assert np.array_equal(idx[0, :int(nb[0])].cpu().numpy(), golden.c2["bad_cols"])
+    x3 = libcalls.load_normalised(golden.mask_input_i16())
+    _, idx, nb = ops.gap_mask(dev(x3[None]), 256, 1724, 0.01, 4, 5)
+    assert np.array_equal(idx[0, :int(nb[0])].cpu().numpy(), golden.c3["bad_cols"])
+
+
+def test_mask_edge_cases(ops):
+    # all silent: every column with a non-empty window is bad; 441000 @ 2048/512 has an empty last window
+    x = np.zeros((1, 441000), np.float32)
+    T, _ = restate.stft_geometry(441000, 2048, 512)
+    _, idx, nb = ops.gap_mask(dev(x), 512, T, 1e-4, 9, 10)
+    assert int(nb[0]) == T - 1 and int(idx[0, T - 2]) == T - 2
+    # nothing silent
+    _, _, nb = ops.gap_mask(dev(np.ones((3, 5000), np.float32)), 256, 21, 1e-4, 9, 10)
+    assert nb.cpu().tolist() == [0, 0, 0]
+
+
+# ---- front / back end (bit-exact) ------------------------------------------------------------------------
+def test_pcm_load_store_bit_exact(ops, golden):
+    pcm = golden.gap_input_i16()
+    x, peak = ops.load_pcm16(dev(pcm[None]))
+    want = libcalls.load_normalised(pcm)
+    assert np.array_equal(x[0].cpu().numpy(), want)
+    assert float(peak[0]) == float(np.max(np.abs(pcm)))
+    rng = np.random.default_rng(0)
+    st = rng.integers(-32768, 32767, (2, 3000, 2)).astype(np.int16)
+    xs, _ = ops.load_pcm16(dev(st))
+    for b in range(2):
+        assert np.array_equal(xs[b].cpu().numpy(), libcalls.load_normalised(st[b]))
+    y = (rng.standard_normal(10000) * 0.6).astype(np.float32)
+    assert np.array_equal(ops.store_pcm16(dev(y)).cpu().numpy(), libcalls.quantise_int16(y))
+
+
+# ---- K4 --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,T,K,iters", [(65, 95, 8, 20), (257, 19, 40, 30), (513, 300, 64, 15), (129, 700, 128, 10),
+                                         (1025, 90, 33, 10)])
+def test_nmf_fit_matches_sklearn_custom_init(ops, F, T, K, iters):
+    rng = np.random.default_rng(F + T)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    W0, Ht0 = restate.init_factors(X.mean(), F, T, K, 0)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, W0=W0, H0=Ht0.T, max_iter=iters, tol=0.0)
+    W, H, err, nit = ops.nmf_fit(dev(X[None]), K, iters, 0.0, 0, dev(W0[None]), dev(np.ascontiguousarray(Ht0.T)[None]))
+    assert int(nit[0]) == no == iters
+    assert abs(float(err[0]) - eo) <= 1e-4 * eo                       # north_star: objective within 1e-4 relative
+    assert rel_l2(W[0].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 1e-3
+
+
+def test_nmf_fit_seeded_init_and_early_stop(ops):
+    """init='random' with random_state: same initial factors as sklearn, same stop iteration (+-1)."""
+    rng = np.random.default_rng(11)
+    F, T, K = 257, 19, 40
+    base = np.abs(rng.standard_normal((F, 6))).astype(np.float32) @ np.abs(rng.standard_normal((6, T))).astype(np.float32)
+    X = (base + 0.01 * np.abs(rng.standard_normal((F, T)))).astype(np.float32)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, seed=0, max_iter=200, tol=1e-4)
+    W, H, err, nit = ops.nmf_fit(dev(X[None]), K, 200, 1e-4, 0, None, None)
+    assert no < 200, "oracle should stop early on this matrix"
+    assert abs(int(nit[0]) - no) <= 2
+    assert abs(float(err[0]) - eo) <= 1e-3 * max(eo, 1e-6) + 1e-6
+    # one iteration from the seeded init must agree tightly
+    Wo1, Ho1, _, _ = libcalls.nmf_fit(X, K, seed=0, max_iter=1, tol=0.0)
+    W1, H1, _, _ = ops.nmf_fit(dev(X[None]), K, 1, 0.0, 0, None, None)
+    assert rel_l2(W1[0].cpu().numpy(), Wo1) < 1e-5 and rel_l2(H1[0].cpu().numpy(), Ho1) < 1e-5
+
+
+def test_nmf_fit_batch_is_independent(ops):
+    rng = np.random.default_rng(5)
+    X = np.abs(rng.standard_normal((3, 129, 200))).astype(np.float32)
+    W, H, err, nit = ops.nmf_fit(dev(X), 16, 12, 0.0, 42, None, None)
+    for b in range(3):
+        Wb, Hb, eb, nb = ops.nmf_fit(dev(X[b:b + 1]), 16, 12, 0.0, 42, None, None)
+        assert torch.equal(W[b], Wb[0]) and torch.equal(H[b], Hb[0])      # deterministic reductions
+        assert float(err[b]) == float(eb[0])
+
+
+def test_nmf_objective_is_monotone(ops):
+    rng = np.random.default_rng(9)
+    X = np.abs(rng.standard_normal((1, 513, 400))).astype(np.float32)
+    errs = [float(ops.nmf_fit(dev(X), 64, it, 0.0, 1, None, None)[2][0]) for it in (1, 2, 4, 8, 16)]
+    assert all(a >= b for a, b in zip(errs, errs[1:]))
+
+
+# ---- end to end: golden vectors ----------------------------------------------------------------------------
+def _run_columns(ops, x, **kw):
+    p = dict(n_fft=1024, hop=256, rank=40, max_iter=200, tol=1e-4, seed=42, threshold=1e-4, frac_num=9, frac_den=10)
+    p.update(kw)
+    out = ops.nmf_inpaint(dev(x[None] if x.ndim == 1 else x), p["n_fft"], p["hop"], p["rank"], p["max_iter"], p["tol"],
+                          p["seed"], p["threshold"], p["frac_num"], p["frac_den"], -1, -1, 1, None, None)
+    return out
+
+
+def test_c2_golden_end_to_end(ops, golden):
+    """main4_NMF_gap.py on demo_assets/part2/damaged_gap.wav vs the shipped fixed_nmf_gap.wav and the oracle."""
+    pcm = golden.gap_input_i16()
+    x = ops.load_pcm16(dev(pcm[None]))[0]
+    y, idx, nb, W, H, err, nit = ops.nmf_inpaint(x, 1024, 256, 40, 200, 1e-4, 42, 1e-4, 9, 10, -1, -1, 1, None, None)
+    c2 = golden.c2
+    n = int(nb[0])
+    assert np.array_equal(idx[0, :n].cpu().numpy(), c2["bad_cols"])                 # bit-exact indices
+    assert int(nit[0]) == int(c2["n_iter"]) == 200
+    assert abs(float(err[0]) - float(c2["err"])) <= 1e-4 * float(c2["err"])         # objective within 1e-4
+    yo, st = libcalls.restore_columns(x[0].cpu().numpy(), SR, return_all=True)
+    yn = y[0].cpu().numpy()
+    gs, ge = c2["gap"]
+    assert libcalls.snr_db(yo, yn) >= 60.0                                         # north_star: >= 60 dB
+    assert libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 40.0
+    shipped = pcm.astype(np.int32) + c2["shipped_minus_input_i16"]
+    q = ops.store_pcm16(y[0]).cpu().numpy().astype(np.int32)
+    outside = np.ones(len(q), bool)
+    outside[gs - 1024:ge + 1024] = False
+    assert np.max(np.abs(q[outside] - shipped[outside])) <= 1                       # untouched region: 1 LSB
+    assert libcalls.snr_db(shipped.astype(np.float64), q.astype(np.float64)) >= 60.0
+
+
+def test_c3_golden_end_to_end(ops, golden):
+    pcm = golden.mask_input_i16()
+    x = ops.load_pcm16(dev(pcm[None]))[0]
+    y, idx, nb, W, H, err, nit = ops.nmf_inpaint(x, 1024, 256, 40, 200, 1e-4, 42, 0.01, 4, 5, -1, -1, 1, None, None)
+    c3 = golden.c3
+    assert np.array_equal(idx[0, :int(nb[0])].cpu().numpy(), c3["bad_cols"])
+    assert int(nit[0]) == int(c3["n_iter"])
+    assert abs(float(err[0]) - float(c3["err"])) <= 1e-4 * float(c3["err"])
+    ref = pcm.astype(np.int32) + c3["ref_minus_input_i16"]
+    q = ops.store_pcm16(y[0]).cpu().numpy().astype(np.int32)
+    assert libcalls.snr_db(ref.astype(np.float64), q.astype(np.float64)) >= 60.0
+
+
+def test_c2_at_2048_512_vs_oracle(ops, golden):
+    """BASELINE config 2 names n_fft=2048 hop=512 (the script hard-codes 1024/256): checked against the oracle."""
+    x = libcalls.load_normalised(golden.gap_input_i16())
+    yo, st = libcalls.restore_columns(x, SR, n_fft=2048, hop=512, return_all=True)
+    y, idx, nb, W, H, err, nit = _run_columns(ops, x, n_fft=2048, hop=512)
+    assert np.array_equal(idx[0, :int(nb[0])].cpu().numpy(), st["bad"]) and int(nb[0]) == 172
+    assert abs(float(err[0]) - st["err"]) <= 1e-4 * st["err"]
+    gs, ge = golden.c2["gap"]
+    yn = y[0].cpu().numpy()
+    assert libcalls.snr_db(yo, yn) >= 60.0 and libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 40.0
+
+
+def test_c1_part0_golden(ops, golden):
+    """main4_NMF.py: 50 refits with early stop, vs the shipped nmf_restored.wav and the reference run."""
+    import ainmf
+    c1 = golden.c1
+    lab = ainmf.SpectralInpainter.__new__(ainmf.SpectralInpainter)
+    ainmf.SpectralInpainter.__init__(lab, filename=None, duration=0.05)
+    lab.sr = int(c1["sr"])
+    lab.raw_audio = c1["raw"].copy()
+    gs, ge = lab.apply_mask(0.2)
+    assert (gs, ge) == tuple(c1["gap"]) and np.array_equal(lab.corrupted_audio, c1["corrupted"])
+    out = lab.restore_with_nmf(n_components=40, n_iter=50)
+    assert lab.cols_ == tuple(c1["cols"]) == (6, 10)
+    assert libcalls.snr_db(c1["restored"], out) >= 60.0
+    assert libcalls.snr_db(c1["restored"][gs:ge], out[gs:ge]) >= 40.0
+    q = libcalls.quantise_int16(out).astype(np.int32)
+    assert np.max(np.abs(q - c1["shipped_restored_i16"].astype(np.int32))) <= 3
+    assert abs(lab.n_iter_ - int(c1["n_iters"][-1])) <= 3
+    assert abs(lab.reconstruction_err_ - float(c1["err"])) <= 0.05 * float(c1["err"]) + 1e-6
+
+
+# ---- edge cases --------------------------------------------------------------------------------------------
+def test_no_bad_frames_returns_input(ops):
+    rng = np.random.default_rng(1)
+    x = (0.5 + 0.1 * rng.standard_normal((2, 30000))).astype(np.float32)
+    x[1, 10000:14000] = 0
+    y, idx, nb, *_ = _run_columns(ops, x, max_iter=5)
+    assert int(nb[0]) == 0 and int(nb[1]) > 0
+    assert np.array_equal(y[0].cpu().numpy(), x[0])            # reference returns self.signal (main4_NMF_gap.py:54)
+    assert not np.array_equal(y[1].cpu().numpy(), x[1])
+
+
+def test_invalid_arguments_raise(ops):
+    import ainmf
+    x = torch.zeros((1, 30000), device="cuda")
+    with pytest.raises(ainmf.AinmfError):
+        ops.stft(x, 1000, 250)                                  # not a power of two
+    with pytest.raises(ainmf.AinmfError):
+        ops.stft(torch.zeros((1, 100), device="cuda"), 1024, 256)   # shorter than one frame
+    with pytest.raises(ainmf.AinmfError):
+        _run_columns(ops, x.cpu().numpy(), rank=500)
+    with pytest.raises(ainmf.AinmfError) as e:
+        _run_columns(ops, np.zeros(30720, np.float32))          # every frame silent (30720 = 120*hop) -> fill undefined
+    assert e.value.code == -5
+    with pytest.raises(NotImplementedError):
+        ops.stft(torch.zeros((1, 4096)), 1024, 256)             # CPU tensor: no CPU implementation
+
+
+def test_shim_classes_match_reference_interface(ops, golden, tmp_path):
+    import ainmf
+    from scipy.io import wavfile
+    path = tmp_path / "damaged_gap.wav"
+    wavfile.write(path, SR, golden.gap_input_i16())
+    lab = ainmf.NMFFairGapInpainter(str(path), output_dir=str(tmp_path))
+    assert lab.restore() is None                                # not loaded yet (main4_NMF_gap.py:43)
+    lab.load_damaged_data()
+    assert lab.sr == SR and lab.signal.dtype == np.float32 and len(lab.signal) == 441000
+    bad = lab.get_gap_mask(1724, 256)
+    assert bad.dtype == np.int64 and np.array_equal(bad, golden.c2["bad_cols"])
+    res = lab.restore()
+    assert res.dtype == np.float32 and res.shape == (441000,)
+    lab.save_result(res)
+    _, saved = wavfile.read(tmp_path / "fixed_nmf_gap.wav")
+    shipped = golden.gap_input_i16().astype(np.int32) + golden.c2["shipped_minus_input_i16"]
+    assert libcalls.snr_db(shipped.astype(np.float64), saved.astype(np.float64)) >= 60.0
+    m = ainmf.NMFFairInpainter(str(path))
+    m.load_damaged_data()
+    assert np.array_equal(m.get_mask_from_signal(1724, 256), libcalls.column_mask(m.signal, 1724, 256, 0.01, 0.8))
