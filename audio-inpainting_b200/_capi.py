@@ -12,8 +12,11 @@ EXPORTS = [
     "ainmf_stft_geometry", "ainmf_padded_rank", "ainmf_stft", "ainmf_gap_mask", "ainmf_nmf_fit", "ainmf_istft",
     "ainmf_workspace_bytes", "ainmf_inpaint", "ainmf_inpaint_host", "ainmf_load_pcm16", "ainmf_store_pcm16",
     "ainmf_comm_unique_id", "ainmf_comm_init", "ainmf_shard_plan", "ainmf_sharded_workspace_bytes",
-    "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile",
+    "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile", "ainmf_comm_set_callbacks",
 ]
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
+SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p)
 
 
 class Params(C.Structure):
@@ -50,6 +53,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "ainmf_profile": (C.c_int, [vp, i32, vp, vp]),
         "ainmf_comm_unique_id": (C.c_int, [vp]),
         "ainmf_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "ainmf_comm_set_callbacks": (C.c_int, [vp, i32, i32, ALLREDUCE_FN, SENDRECV_FN, vp]),
         "ainmf_shard_plan": (C.c_int, [i64, i32, i32, i32, i32, P(i32), P(i32), P(i64), P(i64), P(i64), P(i64)]),
         "ainmf_sharded_workspace_bytes": (sz, [vp, P(Params)]),
         "ainmf_inpaint_sharded": (C.c_int, [vp, P(Params), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -715,3 +715,5 @@ int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pc
 }
 
 }  // extern "C"
+
+#include "sharded.inc"

@@ -132,13 +132,21 @@ struct NmfWork {
     float *violW = nullptr, *violH = nullptr;
     unsigned* counters = nullptr;       // must be zero before the first iteration
     double* err_partial = nullptr;
+    // time-frame-sharded mode only (B == 1); null otherwise
+    float* xht_reduced = nullptr;       // [F][KP]: local X.Ht summed over the splits = first part of the all-reduce buffer
+    double* h_viol_sum = nullptr;       // [B]: local H-side violation, all-reduced by the caller before the stop rule
 };
+enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4 };
 void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk);
 void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
+// the same iteration in pieces, so that a collective can be placed between them (time-sharded mode):
+// PARTIALS: HHt and X.Ht of the local frames; UPDATE: W sweep, WtW, fused X^T.W + H sweep; STOP: the stop rule
+cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s);
+cudaError_t launch_set_err(ClipState* st, int B, const double* err_sq, cudaStream_t s);
 // err = ||X - W H||_F into state[b].err, then bad frames of Xt <- (W H) frames
 cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
-                         cudaStream_t s);
+                         cudaStream_t s, double* err_sq = nullptr);
 
 }  // namespace ainmf

@@ -432,7 +432,7 @@ h_step_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, 
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads)
 stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, int nW,
-            const float* __restrict__ violH, int nH, int it, float tol) {
+            const float* __restrict__ violH, int nH, const double* __restrict__ extra, int it, float tol) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -441,6 +441,7 @@ stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, 
     for (int i = lane; i < nW; i += 32) v += (double)violW[(long long)b * nW + i];
     for (int i = lane; i < nH; i += 32) v += (double)violH[(long long)b * nH + i];
     v = warp_sum_d(v);
+    if (extra) v += extra[b];        // H-side violation already summed over the ranks (time-sharded mode)
     if (lane == 0) {
         ClipState s = st[b];
         s.n_iter = it;
@@ -510,14 +511,27 @@ finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int 
 }
 
 __global__ void __launch_bounds__(kThreads)
-err_reduce_kernel(ClipState* __restrict__ st, int B, const double* __restrict__ err_partial, int n) {
+err_reduce_kernel(ClipState* __restrict__ st, int B, const double* __restrict__ err_partial, int n,
+                  double* __restrict__ err_sq) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
     double v = 0.0;
     for (int i = lane; i < n; i += 32) v += err_partial[(long long)b * n + i];
     v = warp_sum_d(v);
-    if (lane == 0) st[b].err = (float)sqrt(v);
+    if (lane == 0) {
+        if (err_sq) err_sq[b] = v;          // time-sharded mode: the caller all-reduces, then launch_set_err
+        else st[b].err = (float)sqrt(v);
+    }
+}
+__global__ void __launch_bounds__(kThreads)
+set_err_kernel(ClipState* __restrict__ st, int B, const double* __restrict__ err_sq) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) st[b].err = (float)sqrt(err_sq[b]);
+}
+cudaError_t launch_set_err(ClipState* st, int B, const double* err_sq, cudaStream_t s) {
+    AINMF_LAUNCH(set_err_kernel, dim3(ceil_div(B, kThreads)), dim3(kThreads), 0, s, st, B, err_sq);
+    return cudaGetLastError();
 }
 
 // =====================================================================================================
@@ -548,77 +562,123 @@ static cudaError_t run_h_step(const NmfProblem& p, const NmfWork& wk, cudaStream
     return cudaGetLastError();
 }
 
-template <int KP>
-static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
-    constexpr int LW = 8;
-    cudaError_t e;
-    // W half-step
-    prof_begin(PROF_GRAM_H, s);
-    if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
-    prof_end(PROF_GRAM_H, s);
-    const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
-    const int S = ceil_div(p.T, fps);
-    prof_begin(PROF_XHT, s);
-    AINMF_LAUNCH(xht_kernel<KP>, dim3(ceil_div(p.F, 128), S, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf,
-                 p.F, p.T, p.Ht, p.h_stride, fps, wk.xht_partial, p.state);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    prof_end(PROF_XHT, s);
-    {
-        const size_t smem = sizeof(float) * (size_t)KP * (KP + 4 * LW);
-        if ((e = cudaFuncSetAttribute(w_sweep_kernel<KP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        auto kern = w_sweep_kernel<KP, LW>;
-        prof_begin(PROF_W_SWEEP, s);
-        AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(kThreads), smem, s, p.W, p.w_stride, p.F,
-                     wk.HHt, wk.xht_partial, S, wk.violW, p.state);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        prof_end(PROF_W_SWEEP, s);
+// red[f][k] = sum_s partial[s][f][k] (fixed order); used by the time-sharded mode to build the all-reduce buffer
+__global__ void __launch_bounds__(kThreads)
+reduce_partials_kernel(const float* __restrict__ partial, int S, long long n4, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + ((long long)s * n4 + i) * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    // H half-step
-    prof_begin(PROF_GRAM_W, s);
-    if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
-    prof_end(PROF_GRAM_W, s);
-    prof_begin(PROF_H_STEP, s);
-    if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
-    else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s);
-    else e = run_h_step<KP, 128>(p, wk, s);
-    if (e != cudaSuccess) return e;
-    prof_end(PROF_H_STEP, s);
-    prof_begin(PROF_STOP, s);
-    AINMF_LAUNCH(stop_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B, wk.violW,
-                 wk.nW, wk.violH, wk.nH, it, p.tol);
-    e = cudaGetLastError();
-    prof_end(PROF_STOP, s);
-    return e;
+    *reinterpret_cast<float4*>(out + i * 4) = acc;
+}
+// out[b] = sum_i v[b][i] in double (one warp per clip)
+__global__ void __launch_bounds__(kThreads)
+viol_sum_kernel(const float* __restrict__ v, int n, int B, double* __restrict__ out) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += (double)v[(long long)b * n + i];
+    s = warp_sum_d(s);
+    if (lane == 0) out[b] = s;
 }
 
-cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+template <int KP>
+static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s) {
+    constexpr int LW = 8;
+    cudaError_t e;
+    const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
+    const int S = ceil_div(p.T, fps);
+    if (phases & NMF_PHASE_PARTIALS) {
+        // W half-step, local part: Gram of Ht and the X.Ht partial sums
+        prof_begin(PROF_GRAM_H, s);
+        if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
+        prof_end(PROF_GRAM_H, s);
+        prof_begin(PROF_XHT, s);
+        AINMF_LAUNCH(xht_kernel<KP>, dim3(ceil_div(p.F, 128), S, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf,
+                     p.F, p.T, p.Ht, p.h_stride, fps, wk.xht_partial, p.state);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        prof_end(PROF_XHT, s);
+        if (wk.xht_reduced) {     // time-sharded mode (B == 1): one contiguous [F][KP] buffer for the all-reduce
+            const long long n4 = (long long)p.F * KP / 4;
+            AINMF_LAUNCH(reduce_partials_kernel, dim3((unsigned)ceil_div64(n4, kThreads)), dim3(kThreads), 0, s,
+                         wk.xht_partial, S, n4, wk.xht_reduced);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+    }
+    if (phases & NMF_PHASE_UPDATE) {
+        {
+            const size_t smem = sizeof(float) * (size_t)KP * (KP + 4 * LW);
+            if ((e = cudaFuncSetAttribute(w_sweep_kernel<KP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            auto kern = w_sweep_kernel<KP, LW>;
+            prof_begin(PROF_W_SWEEP, s);
+            AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(kThreads), smem, s, p.W, p.w_stride, p.F, wk.HHt,
+                         wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, p.state);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            prof_end(PROF_W_SWEEP, s);
+        }
+        // H half-step
+        prof_begin(PROF_GRAM_W, s);
+        if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
+        prof_end(PROF_GRAM_W, s);
+        prof_begin(PROF_H_STEP, s);
+        if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
+        else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s);
+        else e = run_h_step<KP, 128>(p, wk, s);
+        if (e != cudaSuccess) return e;
+        prof_end(PROF_H_STEP, s);
+        if (wk.h_viol_sum) {      // time-sharded mode: local H-side violation as one double for the all-reduce
+            AINMF_LAUNCH(viol_sum_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, wk.violH, wk.nH,
+                         p.B, wk.h_viol_sum);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+    }
+    if (phases & NMF_PHASE_STOP) {
+        prof_begin(PROF_STOP, s);
+        AINMF_LAUNCH(stop_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B, wk.violW,
+                     wk.nW, wk.violH, wk.h_viol_sum ? 0 : wk.nH, (const double*)wk.h_viol_sum, it, p.tol);
+        e = cudaGetLastError();
+        prof_end(PROF_STOP, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s) {
     switch (p.KP) {
-        case 32: return iterate_impl<32>(p, wk, it, s);
-        case 64: return iterate_impl<64>(p, wk, it, s);
-        case 128: return iterate_impl<128>(p, wk, it, s);
+        case 32: return iterate_impl<32>(p, wk, it, phases, s);
+        case 64: return iterate_impl<64>(p, wk, it, phases, s);
+        case 128: return iterate_impl<128>(p, wk, it, phases, s);
     }
     return (cudaError_t)1;
 }
 
+cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    return nmf_cd_phase(p, wk, it, NMF_PHASE_PARTIALS | NMF_PHASE_UPDATE | NMF_PHASE_STOP, s);
+}
+
 template <int KP>
 static cudaError_t finalize_impl(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad,
-                                 long long bad_stride, cudaStream_t s) {
+                                 long long bad_stride, double* err_sq, cudaStream_t s) {
     const int n = ceil_div(p.T, 16);
     AINMF_LAUNCH(finalize_kernel<KP>, dim3(n, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf, p.F, p.T, p.W,
                  p.w_stride, p.Ht, p.h_stride, bad, bad_stride, wk.err_partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AINMF_LAUNCH(err_reduce_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B,
-                 wk.err_partial, n);
+                 wk.err_partial, n, err_sq);
     return cudaGetLastError();
 }
 
 cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
-                         cudaStream_t s) {
+                         cudaStream_t s, double* err_sq) {
     switch (p.KP) {
-        case 32: return finalize_impl<32>(p, wk, bad, bad_stride, s);
-        case 64: return finalize_impl<64>(p, wk, bad, bad_stride, s);
-        case 128: return finalize_impl<128>(p, wk, bad, bad_stride, s);
+        case 32: return finalize_impl<32>(p, wk, bad, bad_stride, err_sq, s);
+        case 64: return finalize_impl<64>(p, wk, bad, bad_stride, err_sq, s);
+        case 128: return finalize_impl<128>(p, wk, bad, bad_stride, err_sq, s);
     }
     return (cudaError_t)1;
 }

@@ -143,6 +143,13 @@ int ainmf_profile(ainmf_handle h, int32_t enable, double* ms_out, int64_t* count
  * ainmf_comm_unique_id on rank 0 and distributed by the caller (torch.distributed broadcast). */
 int ainmf_comm_unique_id(uint8_t id_out[128]);
 int ainmf_comm_init(ainmf_handle h, const uint8_t unique_id[128], int32_t rank, int32_t nranks);
+/* Alternative transport: the caller supplies the two collectives (used by the CPU test-suite over gloo).
+ * dtype: 0 float32, 1 float64, 2 int32; op: 0 sum, 1 max; peers < 0 mean "none"; return 0 on success. */
+typedef int (*ainmf_allreduce_fn)(void* user, void* buf, size_t count, int dtype, int op, void* stream);
+typedef int (*ainmf_sendrecv_fn)(void* user, const void* sendbuf, int send_peer, void* recvbuf, int recv_peer,
+                                 size_t n_floats, void* stream);
+int ainmf_comm_set_callbacks(ainmf_handle h, int32_t rank, int32_t nranks, ainmf_allreduce_fn allreduce,
+                             ainmf_sendrecv_fn sendrecv, void* user);
 /* Frames [t_begin, t_end) of a T-frame signal owned by `rank`, and the sample range of x that rank needs
  * (its frames' support plus the mask/OLA halo), clipped to [0, N). */
 int ainmf_shard_plan(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t rank, int32_t nranks, int32_t* t_begin,
