@@ -481,6 +481,8 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     impute_carve(base + oI, B, F, &iw);
     nmf_carve(base + oN, B, T, F, KP, &nw);
     unsigned char* nobad = (unsigned char*)(base + oB);
+    TcMaps tcm;
+    if (nmf_tc_setup(pr, &nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     CU(h, cudaMemsetAsync(nw.counters, 0, sizeof(unsigned) * B, s));
     CU(h, cudaMemsetAsync(nobad, 0, (size_t)B * round_up(T, 16), s));
     CU(h, cudaMemsetAsync(pr.state, 0, sizeof(ClipState) * B, s));
@@ -579,6 +581,8 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     pr.W = (float*)(base + pl.off_W); pr.w_stride = pl.w_stride;
     pr.Ht = (float*)(base + pl.off_Ht); pr.h_stride = pl.h_stride;
     pr.state = st;
+    TcMaps tcm;
+    if (nmf_tc_setup(pr, &pl.nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
 
     CU(h, cudaMemsetAsync(pl.nw.counters, 0, sizeof(unsigned) * B, s));
     // a4: STFT

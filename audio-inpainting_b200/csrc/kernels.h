@@ -126,8 +126,16 @@ struct NmfProblem {
     float* Ht; long long h_stride;      // [B][T][KP]
     ClipState* state;                   // [B]
 };
+// TMA tensor maps of the tensor-core path (each an opaque 128-byte CUtensorMap; built on the host per problem)
+struct alignas(64) TcMapBlob { unsigned char b[128]; };
+struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn; };
+
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;
+    // tensor-core path (tcgen05, error-compensated TF32) for the two V-sized contractions; KP in {64,128}
+    int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
+    float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed, and its TF32 residual
+    const TcMaps* tc = nullptr;
     float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
     float *violW = nullptr, *violH = nullptr;
     unsigned* counters = nullptr;       // must be zero before the first iteration
@@ -139,6 +147,10 @@ struct NmfWork {
 enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4 };
 void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk);
+// tensor-core path: build the TMA maps for problem `p` (after nmf_carve) and attach them; 0 on success
+int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* maps);
+cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // X.Ht partials + HHt
+cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // Wt split, X^T.W + H sweep
 void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
 // the same iteration in pieces, so that a collective can be placed between them (time-sharded mode):

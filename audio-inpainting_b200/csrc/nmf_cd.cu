@@ -13,6 +13,8 @@
 #include "kernels.h"
 #include "nmf_cd.cuh"
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace ainmf {
@@ -591,8 +593,19 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     constexpr int LW = 8;
     cudaError_t e;
     const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
-    const int S = ceil_div(p.T, fps);
-    if (phases & NMF_PHASE_PARTIALS) {
+    const int S = wk.use_tc ? wk.tc_splits : ceil_div(p.T, fps);
+    if ((phases & NMF_PHASE_PARTIALS) && wk.use_tc) {
+        // tensor-core path: one kernel yields the X.Ht partials and the Gram of Ht
+        prof_begin(PROF_XHT, s);
+        if ((e = nmf_tc_half1(p, wk, s)) != cudaSuccess) return e;
+        prof_end(PROF_XHT, s);
+        if (wk.xht_reduced) {
+            const long long n4 = (long long)p.F * KP / 4;
+            AINMF_LAUNCH(reduce_partials_kernel, dim3((unsigned)ceil_div64(n4, kThreads)), dim3(kThreads), 0, s,
+                         wk.xht_partial, S, n4, wk.xht_reduced);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+    } else if (phases & NMF_PHASE_PARTIALS) {
         // W half-step, local part: Gram of Ht and the X.Ht partial sums
         prof_begin(PROF_GRAM_H, s);
         if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
@@ -625,7 +638,8 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
         if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
         prof_end(PROF_GRAM_W, s);
         prof_begin(PROF_H_STEP, s);
-        if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
+        if (wk.use_tc) e = nmf_tc_hstep(p, wk, s);
+        else if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
         else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s);
         else e = run_h_step<KP, 128>(p, wk, s);
         if (e != cudaSuccess) return e;
@@ -705,14 +719,32 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
     if (gb < 1) gb = 1;
     if (gb > want) gb = want;
     wk->gram_max_blocks = (int)gb;
+#ifndef AINMF_EMU
+    // tensor-core path for the V-sized contractions (disable with AINMF_DISABLE_TC=1, e.g. to test the FFMA kernels)
+    const char* off = getenv("AINMF_DISABLE_TC");
+    wk->use_tc = (KP >= 64 && T >= 128 && F >= 128 && !(off && off[0] == '1')) ? 1 : 0;
+    if (wk->use_tc) {
+        const int nxs = ceil_div(F, 32);
+        wk->tc_mtiles = ceil_div(32 * nxs + KP, 128);
+        long long sp = (long long)n_sm / ((long long)B * wk->tc_mtiles);
+        if (sp < 1) sp = 1;
+        if (sp > ceil_div(T, 32)) sp = ceil_div(T, 32);
+        wk->tc_fps = round_up(ceil_div(T, (int)sp), 32);
+        wk->tc_splits = ceil_div(T, wk->tc_fps);
+        wk->nH = ceil_div(T, 128);
+    }
+#endif
 }
 
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
     size_t n = 0;
     n += al256(sizeof(float) * (size_t)B * KP * KP) * 2;                          // HHt, WtW
-    n += al256(sizeof(float) * (size_t)B * wk.gram_max_blocks * KP * KP);          // gram partials
+    const int gp = wk.gram_max_blocks > wk.tc_splits ? wk.gram_max_blocks : wk.tc_splits;
+    const int xs = wk.xht_splits > wk.tc_splits ? wk.xht_splits : wk.tc_splits;
+    n += al256(sizeof(float) * (size_t)B * gp * KP * KP);                          // gram partials
     n += al256(sizeof(unsigned) * (size_t)B);                                      // counters
-    n += al256(sizeof(float) * (size_t)B * (wk.xht_splits + 1) * F * KP);           // xht partials
+    n += al256(sizeof(float) * (size_t)B * (xs + 1) * F * KP);                      // xht partials
+    if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)); // Wt, Wt_lo
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
     return n;
@@ -723,12 +755,24 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
     auto take = [&](size_t bytes) { char* r = p; p += al256(bytes); return r; };
     wk->HHt = (float*)take(sizeof(float) * (size_t)B * KP * KP);
     wk->WtW = (float*)take(sizeof(float) * (size_t)B * KP * KP);
-    wk->gram_partial = (float*)take(sizeof(float) * (size_t)B * wk->gram_max_blocks * KP * KP);
+    const int gp = wk->gram_max_blocks > wk->tc_splits ? wk->gram_max_blocks : wk->tc_splits;
+    const int xs = wk->xht_splits > wk->tc_splits ? wk->xht_splits : wk->tc_splits;
+    wk->gram_partial = (float*)take(sizeof(float) * (size_t)B * gp * KP * KP);
     wk->counters = (unsigned*)take(sizeof(unsigned) * (size_t)B);
-    wk->xht_partial = (float*)take(sizeof(float) * (size_t)B * (wk->xht_splits + 1) * F * KP);
+    wk->xht_partial = (float*)take(sizeof(float) * (size_t)B * (xs + 1) * F * KP);
+    if (wk->use_tc) {
+        wk->tc_Wt = (float*)take(sizeof(float) * (size_t)B * KP * round_up(F, 4));
+        wk->tc_WtLo = (float*)take(sizeof(float) * (size_t)B * KP * round_up(F, 4));
+    }
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);
     wk->err_partial = (double*)take(sizeof(double) * (size_t)B * ceil_div(T, 16));
 }
+
+#ifdef AINMF_EMU
+int nmf_tc_setup(const NmfProblem&, NmfWork* wk, TcMaps*) { wk->use_tc = 0; return 0; }
+cudaError_t nmf_tc_half1(const NmfProblem&, const NmfWork&, cudaStream_t) { return (cudaError_t)1; }
+cudaError_t nmf_tc_hstep(const NmfProblem&, const NmfWork&, cudaStream_t) { return (cudaError_t)1; }
+#endif
 
 }  // namespace ainmf

@@ -1,0 +1,416 @@
+// nmf_tc.cu -- the two V-sized contractions of the CD-NMF iteration on the 5th-generation tensor cores (sm_100a):
+//   xht_tc_kernel   : [X | Ht]^T Ht  -> X.Ht partials (F x KP) and the Gram Ht^T Ht (KP x KP), split over time
+//   h_step_tc_kernel: X^T W tile (128 frames x KP) in TMEM -> shared -> the row-parallel CD sweep of nmf_cd.cuh
+// Operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), multiplied with tcgen05.mma kind::tf32 and
+// accumulated in fp32 in TMEM.  A single TF32 pass is not accurate enough for the reference's tolerances
+// (objective drifts 1e-3), so every product is error-compensated:
+//       a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   a_hi = a with the low 13 mantissa bits cleared, a_lo = a - a_hi
+// The tensor core itself ignores the low 13 bits of a 32-bit operand (measured: tests/test_gpu_tc.py), so the raw
+// fp32 tile serves as a_hi; converter warps write a_lo beside it (generic proxy -> fence.proxy.async -> MMA).
+// ncu on the FFMA kernels (profiles/r01_summary.md) shows the path compute-bound at K >= 64, which is the condition
+// north_star sets for using tcgen05 here.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 4-7 = converters and TMEM->register epilogue, then all 8 warps run the sweep.
+#include "kernels.h"
+#include "nmf_cd.cuh"
+#include "tc.cuh"
+
+#ifndef AINMF_EMU
+namespace ainmf {
+using namespace tc;
+
+constexpr int TC_BK = 32;          // contraction elements per stage (one 128-byte row)
+constexpr int TC_M = 128;          // MMA M
+constexpr int TC_CONV_THREADS = 128;
+
+template <int KP> struct TcCfg {
+    static constexpr int NSTAGE = 3;
+    static constexpr int A_BYTES = TC_M * TC_BK * 4;               // 16 KB
+    static constexpr int B_BYTES = KP * TC_BK * 4;                 // 8 / 16 KB
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // raw + lo of both operands
+    static constexpr int L = 4;                                    // sweep lanes per row
+    static constexpr int CPITCH = KP + 4;
+    static constexpr int GPITCH = KP + 4 * L;
+    static constexpr int EPI_BYTES = (TC_M * CPITCH + KP * GPITCH) * 4;
+    static constexpr int PIPE_BYTES = NSTAGE * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + 1024;   // + alignment slack
+};
+
+struct TcBarriers {
+    uint64_t full[4], conv[4], empty[4], accum;
+};
+
+// a_lo = a - trunc_tf32(a) for `n4` float4 of a tile; the raw tile is left in place as a_hi
+__device__ __forceinline__ void write_lo(const float* __restrict__ raw, float* __restrict__ lo, int n4, int tid, int nthreads) {
+    for (int i = tid; i < n4; i += nthreads) {
+        const float4 v = reinterpret_cast<const float4*>(raw)[i];
+        float4 l;
+        float h;
+        split_tf32(v.x, h, l.x); split_tf32(v.y, h, l.y); split_tf32(v.z, h, l.z); split_tf32(v.w, h, l.w);
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+}
+
+// =====================================================================================================
+// h step: grid = (ceil(T/128), B).  A = X tile (K-major, raw + lo by the converters), B = Wt and Wt_lo (K-major,
+// both precomputed by wt_split_kernel).  Stage layout: [A raw][A lo][B raw][B lo].
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWt,
+                 const __grid_constant__ CUtensorMap mapWtLo, int F, int T, const float* __restrict__ G,
+                 float* __restrict__ Ht, long long h_stride, float* __restrict__ viol, const ClipState* __restrict__ st) {
+    using Cfg = TcCfg<KP>;
+    constexpr int L = Cfg::L, SL = KP / L, CPITCH = Cfg::CPITCH;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) TcBarriers bars;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_red[32];
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_M;
+    const int nk = (F + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.conv[s], TC_CONV_THREADS); mbar_init(&bars.empty[s], 1); }
+        mbar_init(&bars.accum, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWt); tma_prefetch_desc(&mapWtLo);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, KP);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+                mbar_wait(&bars.empty[s], ph ^ 1);
+                unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+                tma_load_3d(stg, &mapX, &bars.full[s], i * TC_BK, m0, b);
+                tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapWt, &bars.full[s], i * TC_BK, 0, b);
+                tma_load_3d(stg + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapWtLo, &bars.full[s], i * TC_BK, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, KP, 0, 0);
+            uint32_t acc = 0;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+                mbar_wait(&bars.conv[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+                const uint32_t a_lo = a_raw + Cfg::A_BYTES, b_raw = a_raw + 2 * Cfg::A_BYTES, b_lo = b_raw + Cfg::B_BYTES;
+#pragma unroll
+                for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                    const uint32_t o = k8 * 32;
+                    mma_tf32_ss(tmem, make_smem_desc(a_raw + o, 16, 1024), make_smem_desc(b_raw + o, 16, 1024), idesc, acc);
+                    acc = 1;
+                    mma_tf32_ss(tmem, make_smem_desc(a_raw + o, 16, 1024), make_smem_desc(b_lo + o, 16, 1024), idesc, 1);
+                    mma_tf32_ss(tmem, make_smem_desc(a_lo + o, 16, 1024), make_smem_desc(b_raw + o, 16, 1024), idesc, 1);
+                }
+                mma_commit(&bars.empty[s]);
+            }
+            mma_commit(&bars.accum);
+        }
+    } else if (warp >= 4) {
+        const int ct = threadIdx.x - 128;
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+            mbar_wait(&bars.full[s], ph);
+            const float* raw = reinterpret_cast<const float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
+            write_lo(raw, const_cast<float*>(raw) + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars.conv[s]);
+        }
+    }
+    // ---- epilogue: accumulator -> shared, Gram -> shared, sweep --------------------------------------------
+    float* sC = reinterpret_cast<float*>(smem);                    // [128][CPITCH] (the pipeline buffers are free now)
+    float* sG = sC + TC_M * CPITCH;                                // [KP][GPITCH]
+    mbar_wait(&bars.accum, 0);
+    tcgen05_fence_after();
+    if (warp >= 4) {
+        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < KP; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(sC + row * CPITCH + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    } else {
+        // warps 0-3 stage the Gram matrix meanwhile (disjoint region)
+        constexpr int S = KP / L, PITCH = Cfg::GPITCH;
+        const float* Gb = G + (long long)b * KP * KP;
+        for (int i = threadIdx.x; i < KP * KP / 4; i += 128) {
+            const int t = (4 * i) / KP, r = (4 * i) % KP;
+            *reinterpret_cast<float4*>(sG + t * PITCH + (r / S) * (S + 4) + (r % S)) = *reinterpret_cast<const float4*>(Gb + 4 * i);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, KP);
+
+    constexpr int ROWS = kThreads / L;
+    const int l = threadIdx.x % L;
+    float vsum = 0.f;
+    float* Hb = Ht + (long long)b * h_stride;
+    for (int r0 = 0; r0 < TC_M; r0 += ROWS) {
+        const int r = r0 + threadIdx.x / L;
+        const int t = m0 + r;
+        const bool valid = t < T;
+        float a[SL], bv[SL];
+#pragma unroll
+        for (int q = 0; q < SL; ++q) { a[q] = 0.f; bv[q] = 0.f; }
+        if (valid) {
+            const float* hr = Hb + (long long)t * KP + l * SL;
+            const float* cr = sC + r * CPITCH + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(hr + q);
+                a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
+                const float4 c = *reinterpret_cast<const float4*>(cr + q);
+                bv[q] = c.x; bv[q + 1] = c.y; bv[q + 2] = c.z; bv[q + 3] = c.w;
+            }
+        }
+        vsum += cd_sweep_row<KP, L>(a, bv, sG, l, valid);
+        if (valid) {
+            float* hr = Hb + (long long)t * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(hr + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+        }
+    }
+    const float tot = block_sum(vsum, s_red);
+    if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+}
+
+// =====================================================================================================
+// xht + gram: grid = (m_tiles, S, B).  Both operands are MN-major (time is the slow dimension of Xt and Ht), which
+// for tf32 requires the 32-byte-atom 128B swizzle.  The A operand of tile `mt` is the list of 32-column slabs
+// v = 4*mt + j of the virtual matrix [ X (ceil(F/32) slabs) | Ht (KP/32 slabs) ]; slabs past the end load zeros.
+// Stage layout: [A raw (4 slabs)][A lo][B raw (KP/32 slabs)][B lo]; both lo tiles come from the converters.
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant__ CUtensorMap mapHmn, int F, int T,
+              int frames_per_split, float* __restrict__ xht_partial /*[B][S][F][KP]*/,
+              float* __restrict__ gram_partial /*[B][S][KP][KP]*/, const ClipState* __restrict__ st) {
+    using Cfg = TcCfg<KP>;
+    constexpr int SLAB = 32 * TC_BK * 4;                           // 4 KB: 32 columns x 32 frames
+    constexpr int NB = KP / 32;                                    // B slabs
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) TcBarriers bars;
+    __shared__ uint32_t tmem_slot;
+    const int b = blockIdx.z, split = blockIdx.y, S = gridDim.y, mt = blockIdx.x;
+    if (st[b].done) return;
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nxs = (F + 31) / 32;                                 // X slabs of the virtual matrix
+    const int t_begin = split * frames_per_split;
+    const int t_end = min(T, t_begin + frames_per_split);
+    const int nk = (t_end - t_begin + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.conv[s], TC_CONV_THREADS); mbar_init(&bars.empty[s], 1); }
+        mbar_init(&bars.accum, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapXmn); tma_prefetch_desc(&mapHmn);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, KP);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+                mbar_wait(&bars.empty[s], ph ^ 1);
+                unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
+                const int t0 = t_begin + i * TC_BK;
+                // rows past t_end of this split must not contribute: the split boundary is a multiple of 32 except
+                // at T, where TMA zero-fills (d1 = T)
+                mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int v = 4 * mt + j;
+                    if (v < nxs) tma_load_3d(stg + j * SLAB, &mapXmn, &bars.full[s], 32 * v, t0, b);
+                    else tma_load_3d(stg + j * SLAB, &mapHmn, &bars.full[s], 32 * (v - nxs), t0, b);   // >= KP: zero fill
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) tma_load_3d(stg + 2 * Cfg::A_BYTES + j * SLAB, &mapHmn, &bars.full[s], 32 * j, t0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, KP, 1, 1);
+            uint32_t acc = 0;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+                mbar_wait(&bars.conv[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+                const uint32_t a_lo = a_raw + Cfg::A_BYTES, b_raw = a_raw + 2 * Cfg::A_BYTES, b_lo = b_raw + Cfg::B_BYTES;
+#pragma unroll
+                for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                    const uint32_t o = k8 * 1024;                  // 8 frames x 128 B
+                    const uint64_t dar = make_smem_desc(a_raw + o, SLAB, 512, kLayoutSw128Base32);
+                    const uint64_t dal = make_smem_desc(a_lo + o, SLAB, 512, kLayoutSw128Base32);
+                    const uint64_t dbr = make_smem_desc(b_raw + o, SLAB, 512, kLayoutSw128Base32);
+                    const uint64_t dbl = make_smem_desc(b_lo + o, SLAB, 512, kLayoutSw128Base32);
+                    mma_tf32_ss(tmem, dar, dbr, idesc, acc);
+                    acc = 1;
+                    mma_tf32_ss(tmem, dar, dbl, idesc, 1);
+                    mma_tf32_ss(tmem, dal, dbr, idesc, 1);
+                }
+                mma_commit(&bars.empty[s]);
+            }
+            mma_commit(&bars.accum);
+        }
+    } else if (warp >= 4) {
+        const int ct = threadIdx.x - 128;
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
+            mbar_wait(&bars.full[s], ph);
+            float* raw = reinterpret_cast<float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
+            write_lo(raw, raw + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
+            write_lo(raw + 2 * Cfg::A_BYTES / 4, raw + (2 * Cfg::A_BYTES + Cfg::B_BYTES) / 4, Cfg::B_BYTES / 16, ct, TC_CONV_THREADS);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars.conv[s]);
+        }
+    }
+    // ---- epilogue: rows of the accumulator straight to the partial buffers -------------------------------
+    if (nk > 0) mbar_wait(&bars.accum, 0);
+    tcgen05_fence_after();
+    if (warp >= 4) {
+        const int q = warp & 3;
+        const int vcol = 128 * mt + q * 32 + lane;                 // virtual column = output row
+        float* dst = nullptr;
+        if (vcol < 32 * nxs) {
+            if (vcol < F) dst = xht_partial + ((((long long)b * S + split) * F) + vcol) * KP;
+        } else if (vcol - 32 * nxs < KP) {
+            dst = gram_partial + ((((long long)b * S + split) * KP) + (vcol - 32 * nxs)) * KP;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < KP; c0 += 32) {
+            float v[32];
+            if (nk > 0) {
+                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (dst) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, KP);
+}
+
+// Wt[b][k][f] = W[b][f][k] and Wt_lo = Wt - trunc_tf32(Wt); 32x32 tiles; grid = (ceil(F/32), KP/32, B)
+__global__ void __launch_bounds__(kThreads)
+wt_split_kernel(const float* __restrict__ W, long long w_stride, int F, int KP, int ldw, float* __restrict__ Wt,
+                float* __restrict__ WtLo, long long wt_stride, const ClipState* __restrict__ st) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    if (st[b].done) return;
+    const int f0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int r = ly; r < 32; r += 8) {
+        const int f = f0 + r;
+        tile[r][lx] = (f < F) ? W[(long long)b * w_stride + (long long)f * KP + k0 + lx] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ly; r < 32; r += 8) {
+        const int k = k0 + r, f = f0 + lx;
+        if (f < ldw) {
+            const float v = tile[lx][r];
+            float h, l;
+            split_tf32(v, h, l);
+            Wt[(long long)b * wt_stride + (long long)k * ldw + f] = v;
+            WtLo[(long long)b * wt_stride + (long long)k * ldw + f] = l;
+        }
+    }
+}
+
+// out[b][e] = sum_s partial[b][s][e]  (fixed order); grid = (ceil(n4/256), B)
+__global__ void __launch_bounds__(kThreads)
+reduce_splits_kernel(const float* __restrict__ partial, int S, long long n4, float* __restrict__ out, long long out_stride,
+                     const ClipState* __restrict__ st) {
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + (((long long)b * S + s) * n4 + i) * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (long long)b * out_stride + i * 4) = acc;
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------
+static_assert(sizeof(CUtensorMap) == sizeof(TcMapBlob), "CUtensorMap is 128 bytes");
+static inline const CUtensorMap& as_map(const TcMapBlob& b) { return *reinterpret_cast<const CUtensorMap*>(&b); }
+static inline CUtensorMap* as_map_ptr(TcMapBlob* b) { return reinterpret_cast<CUtensorMap*>(b); }
+template <int KP>
+static cudaError_t tc_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    using Cfg = TcCfg<KP>;
+    cudaError_t e = cudaFuncSetAttribute(xht_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    const int S = wk.tc_splits;
+    AINMF_LAUNCH(xht_tc_kernel<KP>, dim3(wk.tc_mtiles, S, p.B), dim3(kThreads), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXmn),
+                 as_map(wk.tc->mapHmn), p.F, p.T, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const long long n4 = (long long)KP * KP / 4;
+    AINMF_LAUNCH(reduce_splits_kernel, dim3((unsigned)ceil_div64(n4, kThreads), p.B), dim3(kThreads), 0, s, wk.gram_partial, S,
+                 n4, wk.HHt, (long long)KP * KP, p.state);
+    return cudaGetLastError();
+}
+cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    return p.KP == 64 ? tc_half1_impl<64>(p, wk, s) : tc_half1_impl<128>(p, wk, s);
+}
+
+template <int KP>
+static cudaError_t tc_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    using Cfg = TcCfg<KP>;
+    const int ldw = p.ldf;
+    AINMF_LAUNCH(wt_split_kernel, dim3(ceil_div(ldw, 32), KP / 32, p.B), dim3(kThreads), 0, s, p.W, p.w_stride, p.F, KP, ldw,
+                 wk.tc_Wt, wk.tc_WtLo, (long long)KP * ldw, p.state);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(h_step_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
+    AINMF_LAUNCH(h_step_tc_kernel<KP>, dim3(ceil_div(p.T, TC_M), p.B), dim3(kThreads), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX),
+                 as_map(wk.tc->mapWt), as_map(wk.tc->mapWtLo), p.F, p.T, wk.WtW, p.Ht, p.h_stride, wk.violH, p.state);
+    return cudaGetLastError();
+}
+cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    return p.KP == 64 ? tc_hstep_impl<64>(p, wk, s) : tc_hstep_impl<128>(p, wk, s);
+}
+
+int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* m) {
+    if (!wk->use_tc) return 0;
+    const uint64_t B = p.B, T = p.T, F = p.F, ldf = p.ldf, KP = p.KP;
+    int rc = make_tensor_map_3d(as_map_ptr(&m->mapX), p.Xt, F, T, B, ldf, (uint64_t)p.x_stride, TC_BK, TC_M, 0);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapWt), wk->tc_Wt, F, KP, B, ldf, KP * ldf, TC_BK, (uint32_t)KP, 0);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapWtLo), wk->tc_WtLo, F, KP, B, ldf, KP * ldf, TC_BK, (uint32_t)KP, 0);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapXmn), p.Xt, F, T, B, ldf, (uint64_t)p.x_stride, 32, TC_BK, 1);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapHmn), p.Ht, KP, T, B, KP, (uint64_t)p.h_stride, 32, TC_BK, 1);
+    wk->tc = m;
+    return rc;
+}
+
+}  // namespace ainmf
+#endif  // AINMF_EMU

@@ -1,0 +1,132 @@
+// tc_probe.cu -- diagnostic single-CTA GEMM that exercises exactly the TMA / descriptor / tcgen05 / TMEM encodings
+// the tensor-core NMF kernels rely on (K-major and MN-major operands, SWIZZLE_128B, kind::tf32, 3-pass split).
+// Exported as ainmf_tc_probe for tests/test_gpu_tc.py; not part of the inpainting path.
+#include <stdio.h>
+
+#include "tc.cuh"
+
+#ifndef AINMF_EMU
+namespace ainmf {
+using namespace tc;
+
+constexpr int PM = 128;       // M
+constexpr int PBK = 32;       // contraction elements per stage (one 128-byte swizzle row)
+
+// mode 0: A [128][Kd], B [N][Kd]  (K-major both);  mode 1: At [Kd][128], Bt [Kd][N] (MN-major both)
+// split: 0 = single pass on the raw fp32 bits; 1 = hi/lo split in shared memory + 3 passes
+template <int N>
+__global__ void __launch_bounds__(128)
+tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Kd, int mode,
+                int split, float* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int stages = Kd / PBK;
+    const uint32_t a_bytes = PM * PBK * 4, b_bytes = N * PBK * 4;
+    float* sA = reinterpret_cast<float*>(smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));   // 1024-B aligned, [stages][a]
+    float* sB = sA + (size_t)stages * PM * PBK;                          // [stages][b]
+    float* sAlo = sB + (size_t)stages * N * PBK;
+    float* sBlo = sAlo + (size_t)stages * PM * PBK;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_full, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, N < 32 ? 32 : N);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar_full, (uint32_t)stages * (a_bytes + b_bytes));
+        for (int s = 0; s < stages; ++s) {
+            if (mode == 0) {
+                tma_load_3d(sA + (size_t)s * PM * PBK, &mapA, &bar_full, s * PBK, 0, 0);
+                tma_load_3d(sB + (size_t)s * N * PBK, &mapB, &bar_full, s * PBK, 0, 0);
+            } else {
+                for (int j = 0; j < PM / 32; ++j)
+                    tma_load_3d(sA + (size_t)s * PM * PBK + j * (32 * PBK), &mapA, &bar_full, j * 32, s * PBK, 0);
+                for (int j = 0; j < N / 32; ++j)
+                    tma_load_3d(sB + (size_t)s * N * PBK + j * (32 * PBK), &mapB, &bar_full, j * 32, s * PBK, 0);
+            }
+        }
+    }
+    mbar_wait(&bar_full, 0);
+    if (split) {       // generic-proxy rewrite of the tiles: hi in place, lo beside; then make it visible to the MMA
+        const int na = stages * PM * PBK, nb = stages * N * PBK;
+        for (int i = threadIdx.x; i < na; i += blockDim.x) { float h, l; split_tf32(sA[i], h, l); sA[i] = h; sAlo[i] = l; }
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) { float h, l; split_tf32(sB[i], h, l); sB[i] = h; sBlo[i] = l; }
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_tf32(PM, N, mode, mode);
+        uint32_t acc = 0;
+        for (int s = 0; s < stages; ++s) {
+            for (int k8 = 0; k8 < PBK / 8; ++k8) {
+                const int passes = split ? 3 : 1;
+                for (int pss = 0; pss < passes; ++pss) {
+                    const float* a = (pss == 2 ? sAlo : sA) + (size_t)s * PM * PBK;
+                    const float* b = (pss == 1 ? sBlo : sB) + (size_t)s * N * PBK;
+                    uint64_t da, db;
+                    if (mode == 0) {
+                        da = make_smem_desc(smem_u32(a) + k8 * 32, 16, 1024);
+                        db = make_smem_desc(smem_u32(b) + k8 * 32, 16, 1024);
+                    } else {
+                        da = make_smem_desc(smem_u32(a) + k8 * 1024, 32 * PBK * 4, 512, kLayoutSw128Base32);
+                        db = make_smem_desc(smem_u32(b) + k8 * 1024, 32 * PBK * 4, 512, kLayoutSw128Base32);
+                    }
+                    mma_tf32_ss(tmem, da, db, idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+        mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tcgen05_fence_after();
+    // warp w owns TMEM lanes 32w .. 32w+31 = rows of D
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        const int row = warp * 32 + (threadIdx.x & 31);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) D[(size_t)row * N + c0 + j] = v[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, N < 32 ? 32 : N);
+}
+
+}  // namespace ainmf
+
+extern "C" int ainmf_tc_probe(int mode, int split, int N, int Kd, const float* A, const float* B, float* D, void* stream) {
+    using namespace ainmf;
+    if ((N != 64 && N != 128) || Kd % PBK != 0 || Kd <= 0 || Kd > 128) return -1;
+    CUtensorMap ma, mb;
+    int rc;
+    if (mode == 0) {
+        rc = make_tensor_map_3d(&ma, A, Kd, PM, 1, Kd, (uint64_t)Kd * PM, PBK, PM);
+        if (!rc) rc = make_tensor_map_3d(&mb, B, Kd, N, 1, Kd, (uint64_t)Kd * N, PBK, N);
+    } else {
+        rc = make_tensor_map_3d(&ma, A, PM, Kd, 1, PM, (uint64_t)Kd * PM, 32, PBK, 1);
+        if (!rc) rc = make_tensor_map_3d(&mb, B, N, Kd, 1, N, (uint64_t)Kd * N, 32, PBK, 1);
+    }
+    if (rc) return 1000 + rc;
+    const int stages = Kd / PBK;
+    const size_t smem = 2 * (size_t)stages * (PM + N) * PBK * 4 + 1024;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (N == 64) {
+        e = cudaFuncSetAttribute(tc_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) tc_probe_kernel<64><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D);
+    } else {
+        e = cudaFuncSetAttribute(tc_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) tc_probe_kernel<128><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D);
+    }
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+#endif
