@@ -128,7 +128,7 @@ struct NmfProblem {
 };
 // TMA tensor maps of the tensor-core path (each an opaque 128-byte CUtensorMap; built on the host per problem)
 struct alignas(64) TcMapBlob { unsigned char b[128]; };
-struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn; };
+struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn, mapHk, mapG; };
 
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;

@@ -12,6 +12,8 @@
 // warps 4-7 = converters and TMEM->register epilogue, then all 8 warps run the sweep.
 #include "kernels.h"
 #include "nmf_cd.cuh"
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 #ifndef AINMF_EMU
@@ -20,47 +22,75 @@ using namespace tc;
 
 constexpr int TC_BK = 32;          // contraction elements per stage (one 128-byte row)
 constexpr int TC_M = 128;          // MMA M
-constexpr int TC_CONV_THREADS = 128;
+constexpr int TC_CONV_THREADS = 192;   // warps 2..7
 
-template <int KP> struct TcCfg {
-    static constexpr int NSTAGE = 3;
+// NSTAGE: h step KP=64 uses 2 stages (96 KB) so that two blocks share an SM and one block's sweep overlaps the
+// other's GEMM; KP=128 needs 64 KB per stage and runs one block per SM with 3 stages.
+template <int KP, int NSTAGE_> struct TcCfg {
+    static constexpr int NSTAGE = NSTAGE_;
     static constexpr int A_BYTES = TC_M * TC_BK * 4;               // 16 KB
     static constexpr int B_BYTES = KP * TC_BK * 4;                 // 8 / 16 KB
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // raw + lo of both operands
-    static constexpr int L = 4;                                    // sweep lanes per row
+    static constexpr int L = 8, R = 4;                             // sweep: 8 lanes x 4 frames per group, one pass
     static constexpr int CPITCH = KP + 4;
     static constexpr int GPITCH = KP + 4 * L;
-    static constexpr int EPI_BYTES = (TC_M * CPITCH + KP * GPITCH) * 4;
+    static constexpr int EPI_BYTES = (TC_M * CPITCH + KP * GPITCH + KP) * 4;
     static constexpr int PIPE_BYTES = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + 1024;   // + alignment slack
 };
+template <int KP> struct HStepStages { static constexpr int value = (KP == 64) ? 2 : 3; };
+template <int KP> struct XhtStages { static constexpr int value = (KP == 64) ? 4 : 3; };
 
 struct TcBarriers {
     uint64_t full[4], conv[4], empty[4], accum;
 };
 
-// a_lo = a - trunc_tf32(a) for `n4` float4 of a tile; the raw tile is left in place as a_hi
+// a_lo = a - trunc_tf32(a) for `n4` float4 of a tile; the raw tile is left in place as a_hi.  Loads are issued in
+// batches of 4 before the dependent arithmetic so that the shared-memory latency is paid once per batch.
 __device__ __forceinline__ void write_lo(const float* __restrict__ raw, float* __restrict__ lo, int n4, int tid, int nthreads) {
-    for (int i = tid; i < n4; i += nthreads) {
-        const float4 v = reinterpret_cast<const float4*>(raw)[i];
+    const float4* src = reinterpret_cast<const float4*>(raw);
+    float4* dst = reinterpret_cast<float4*>(lo);
+    int i = tid;
+    for (; i + 3 * nthreads < n4; i += 4 * nthreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = src[i + u * nthreads];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float4 l;
+            float h;
+            split_tf32(v[u].x, h, l.x); split_tf32(v[u].y, h, l.y); split_tf32(v[u].z, h, l.z); split_tf32(v[u].w, h, l.w);
+            dst[i + u * nthreads] = l;
+        }
+    }
+    for (; i < n4; i += nthreads) {
+        const float4 v = src[i];
         float4 l;
         float h;
         split_tf32(v.x, h, l.x); split_tf32(v.y, h, l.y); split_tf32(v.z, h, l.z); split_tf32(v.w, h, l.w);
-        reinterpret_cast<float4*>(lo)[i] = l;
+        dst[i] = l;
     }
 }
 
 // =====================================================================================================
-// h step: grid = (ceil(T/128), B).  A = X tile (K-major, raw + lo by the converters), B = Wt and Wt_lo (K-major,
-// both precomputed by wt_split_kernel).  Stage layout: [A raw][A lo][B raw][B lo].
+// h step: grid = (ceil(T/128), B).  The accumulator collects  D = X_tile.W  -  Ht_tile.(W^T W)  = -(gradient of the
+// H half-step at the old Ht), so the sweep starts from the gradient and never recomputes a dot product:
+//   stages 0 .. nkX-1      : A = X chunk (K-major; raw + lo by the converters), B = Wt, Wt_lo chunks (precomputed)
+//   stages nkX .. nkX+KP/32: A = Ht chunk (K-major), B = W^T W chunk; both lo tiles by the converters; A negated
+// Stage layout: [A raw][A lo][B raw][B lo].
 // =====================================================================================================
 template <int KP>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (KP == 64) ? 2 : 1)
 h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWt,
-                 const __grid_constant__ CUtensorMap mapWtLo, int F, int T, const float* __restrict__ G,
-                 float* __restrict__ Ht, long long h_stride, float* __restrict__ viol, const ClipState* __restrict__ st) {
-    using Cfg = TcCfg<KP>;
-    constexpr int L = Cfg::L, SL = KP / L, CPITCH = Cfg::CPITCH;
+                 const __grid_constant__ CUtensorMap mapWtLo, const __grid_constant__ CUtensorMap mapHk,
+                 const __grid_constant__ CUtensorMap mapG, int F, int T, const float* __restrict__ G,
+                 float* __restrict__ Ht, long long h_stride, float* __restrict__ viol, const ClipState* __restrict__ st,
+                 long long* __restrict__ dbg) {
+    using Cfg = TcCfg<KP, HStepStages<KP>::value>;
+    constexpr int L = Cfg::L, R = Cfg::R, SL = KP / L, CPITCH = Cfg::CPITCH;
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;
+    const long long dbg_t0 = clock64();
+#define DBG(slot) do { if (dbg_on) dbg[slot] = clock64() - dbg_t0; } while (0)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) TcBarriers bars;
     __shared__ uint32_t tmem_slot;
@@ -70,13 +100,14 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_M;
-    const int nk = (F + TC_BK - 1) / TC_BK;
+    const int nkX = (F + TC_BK - 1) / TC_BK;
+    const int nk = nkX + KP / TC_BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.conv[s], TC_CONV_THREADS); mbar_init(&bars.empty[s], 1); }
         mbar_init(&bars.accum, 1);
         mbar_fence_init();
-        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWt); tma_prefetch_desc(&mapWtLo);
+        tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWt); tma_prefetch_desc(&mapWtLo); tma_prefetch_desc(&mapHk); tma_prefetch_desc(&mapG);
     }
     if (warp == 1) tmem_alloc(&tmem_slot, KP);
     tcgen05_fence_before();
@@ -84,56 +115,85 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
 
+    // Role loops.  Whole warps iterate (only lane 0 of warps 0/1 acts) so that the other lanes wait at the warp
+    // barrier instead of polling an mbarrier and stealing issue slots from the converters.
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nk; ++i) {
+        for (int i = 0; i < nk; ++i) {
+            if (lane == 0) {
                 const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
                 mbar_wait(&bars.empty[s], ph ^ 1);
+                DBG(8 + 6 * i + 5);
                 unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
-                mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
-                tma_load_3d(stg, &mapX, &bars.full[s], i * TC_BK, m0, b);
-                tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapWt, &bars.full[s], i * TC_BK, 0, b);
-                tma_load_3d(stg + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapWtLo, &bars.full[s], i * TC_BK, 0, b);
+                if (i < nkX) {
+                    mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+                    tma_load_3d(stg, &mapX, &bars.full[s], i * TC_BK, m0, b);
+                    tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapWt, &bars.full[s], i * TC_BK, 0, b);
+                    tma_load_3d(stg + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapWtLo, &bars.full[s], i * TC_BK, 0, b);
+                } else {
+                    mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_3d(stg, &mapHk, &bars.full[s], (i - nkX) * TC_BK, m0, b);
+                    tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapG, &bars.full[s], (i - nkX) * TC_BK, 0, b);
+                }
+                DBG(8 + 6 * i + 0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, KP, 0, 0);
-            uint32_t acc = 0;
-            for (int i = 0; i < nk; ++i) {
+        const uint32_t idesc = make_idesc_tf32(TC_M, KP, 0, 0);
+        const uint32_t idesc_neg = idesc | (1u << 13);              // negate A: subtracts Ht.(W^T W)
+        uint32_t acc = 0;
+        for (int i = 0; i < nk; ++i) {
+            if (lane == 0) {
                 const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
                 mbar_wait(&bars.conv[s], ph);
+                DBG(8 + 6 * i + 4);
                 tcgen05_fence_after();
                 const uint32_t a_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
-                const uint32_t a_lo = a_raw + Cfg::A_BYTES, b_raw = a_raw + 2 * Cfg::A_BYTES, b_lo = b_raw + Cfg::B_BYTES;
+                const uint32_t id = (i < nkX) ? idesc : idesc_neg;
+                // descriptors differ only in the 14-bit start-address field: build one, add byte offsets >> 4
+                const uint64_t d_ar = make_smem_desc(a_raw, 16, 1024);
+                const uint64_t d_al = d_ar + (uint64_t)(Cfg::A_BYTES >> 4);
+                const uint64_t d_br = d_ar + (uint64_t)((2 * Cfg::A_BYTES) >> 4);
+                const uint64_t d_bl = d_br + (uint64_t)(Cfg::B_BYTES >> 4);
 #pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-                    const uint32_t o = k8 * 32;
-                    mma_tf32_ss(tmem, make_smem_desc(a_raw + o, 16, 1024), make_smem_desc(b_raw + o, 16, 1024), idesc, acc);
+                    const uint64_t o = (uint64_t)(k8 * 32 >> 4);
+                    mma_tf32_ss(tmem, d_ar + o, d_br + o, id, acc);
                     acc = 1;
-                    mma_tf32_ss(tmem, make_smem_desc(a_raw + o, 16, 1024), make_smem_desc(b_lo + o, 16, 1024), idesc, 1);
-                    mma_tf32_ss(tmem, make_smem_desc(a_lo + o, 16, 1024), make_smem_desc(b_raw + o, 16, 1024), idesc, 1);
+                    mma_tf32_ss(tmem, d_ar + o, d_bl + o, id, 1);
+                    mma_tf32_ss(tmem, d_al + o, d_br + o, id, 1);
                 }
                 mma_commit(&bars.empty[s]);
+                if (i == nk - 1) mma_commit(&bars.accum);
+                DBG(8 + 6 * i + 3);
             }
-            mma_commit(&bars.accum);
+            __syncwarp();
         }
-    } else if (warp >= 4) {
-        const int ct = threadIdx.x - 128;
+    } else {
+        const int ct = threadIdx.x - 64;
         for (int i = 0; i < nk; ++i) {
             const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
-            mbar_wait(&bars.full[s], ph);
-            const float* raw = reinterpret_cast<const float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
-            write_lo(raw, const_cast<float*>(raw) + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
+            if (lane == 0) mbar_wait(&bars.full[s], ph);     // one poller per warp; the other lanes sleep at the warp barrier
+            __syncwarp();
+            if (ct == 0) DBG(8 + 6 * i + 1);
+            float* raw = reinterpret_cast<float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
+            write_lo(raw, raw + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
+            if (i >= nkX) write_lo(raw + 2 * Cfg::A_BYTES / 4, raw + (2 * Cfg::A_BYTES + Cfg::B_BYTES) / 4, Cfg::B_BYTES / 16, ct, TC_CONV_THREADS);
             fence_proxy_async_smem();
             mbar_arrive(&bars.conv[s]);
+            if (ct == 0) DBG(8 + 6 * i + 2);
         }
     }
+    if (threadIdx.x == 0) DBG(0);
     // ---- epilogue: accumulator -> shared, Gram -> shared, sweep --------------------------------------------
-    float* sC = reinterpret_cast<float*>(smem);                    // [128][CPITCH] (the pipeline buffers are free now)
+    float* sC = reinterpret_cast<float*>(smem);                    // [128][CPITCH] (aliases the pipeline buffers)
     float* sG = sC + TC_M * CPITCH;                                // [KP][GPITCH]
-    mbar_wait(&bars.accum, 0);
+    float* sInv = sG + KP * Cfg::GPITCH;                           // [KP] reciprocal of the Gram diagonal
+    __syncthreads();                                               // idle lanes park here (hardware barrier, no polling)
+    if (lane == 0) mbar_wait(&bars.accum, 0);                      // every MMA has finished reading the stage buffers
+    __syncwarp();
     tcgen05_fence_after();
+    if (threadIdx.x == 0) DBG(1);
     if (warp >= 4) {
         const int q = warp & 3;                                    // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
@@ -153,42 +213,49 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const int t = (4 * i) / KP, r = (4 * i) % KP;
             *reinterpret_cast<float4*>(sG + t * PITCH + (r / S) * (S + 4) + (r % S)) = *reinterpret_cast<const float4*>(Gb + 4 * i);
         }
+        for (int t = threadIdx.x; t < KP; t += 128) {
+            const float d = Gb[t * KP + t];
+            sInv[t] = (d != 0.f) ? 1.0f / d : 0.f;
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, KP);
+    if (threadIdx.x == 0) DBG(2);
 
-    constexpr int ROWS = kThreads / L;
-    const int l = threadIdx.x % L;
-    float vsum = 0.f;
+    // sweep: a group of L lanes owns R consecutive frames; 256 threads = 32 groups x 4 frames = the 128-frame tile
+    const int l = threadIdx.x % L, grp = threadIdx.x / L;
     float* Hb = Ht + (long long)b * h_stride;
-    for (int r0 = 0; r0 < TC_M; r0 += ROWS) {
-        const int r = r0 + threadIdx.x / L;
+    float a[R][SL], g[R][SL];
+    bool valid[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int r = grp * R + i;
         const int t = m0 + r;
-        const bool valid = t < T;
-        float a[SL], bv[SL];
+        valid[i] = t < T;
+        const float* cr = sC + r * CPITCH + l * SL;
 #pragma unroll
-        for (int q = 0; q < SL; ++q) { a[q] = 0.f; bv[q] = 0.f; }
-        if (valid) {
-            const float* hr = Hb + (long long)t * KP + l * SL;
-            const float* cr = sC + r * CPITCH + l * SL;
-#pragma unroll
-            for (int q = 0; q < SL; q += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(hr + q);
-                a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
-                const float4 c = *reinterpret_cast<const float4*>(cr + q);
-                bv[q] = c.x; bv[q + 1] = c.y; bv[q + 2] = c.z; bv[q + 3] = c.w;
-            }
+        for (int q = 0; q < SL; q += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[i]) v = *reinterpret_cast<const float4*>(Hb + (long long)t * KP + l * SL + q);
+            a[i][q] = v.x; a[i][q + 1] = v.y; a[i][q + 2] = v.z; a[i][q + 3] = v.w;
+            const float4 c = *reinterpret_cast<const float4*>(cr + q);
+            g[i][q] = -c.x; g[i][q + 1] = -c.y; g[i][q + 2] = -c.z; g[i][q + 3] = -c.w;      // gradient = -(accumulator)
         }
-        vsum += cd_sweep_row<KP, L>(a, bv, sG, l, valid);
-        if (valid) {
-            float* hr = Hb + (long long)t * KP + l * SL;
+    }
+    const float vsum = cd_sweep_rows_inc<KP, L, R>(a, g, sG, sInv, l, valid);
 #pragma unroll
-            for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(hr + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+    for (int i = 0; i < R; ++i) {
+        if (valid[i]) {
+            float* hr = Hb + (long long)(m0 + grp * R + i) * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(hr + q) = make_float4(a[i][q], a[i][q + 1], a[i][q + 2], a[i][q + 3]);
         }
     }
     const float tot = block_sum(vsum, s_red);
     if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+    if (threadIdx.x == 0) DBG(3);
+#undef DBG
 }
 
 // =====================================================================================================
@@ -202,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant__ CUtensorMap mapHmn, int F, int T,
               int frames_per_split, float* __restrict__ xht_partial /*[B][S][F][KP]*/,
               float* __restrict__ gram_partial /*[B][S][KP][KP]*/, const ClipState* __restrict__ st) {
-    using Cfg = TcCfg<KP>;
+    using Cfg = TcCfg<KP, XhtStages<KP>::value>;
     constexpr int SLAB = 32 * TC_BK * 4;                           // 4 KB: 32 columns x 32 frames
     constexpr int NB = KP / 32;                                    // B slabs
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -230,8 +297,8 @@ xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant_
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nk; ++i) {
+        for (int i = 0; i < nk; ++i) {
+            if (lane == 0) {
                 const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
                 mbar_wait(&bars.empty[s], ph ^ 1);
                 unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
@@ -248,12 +315,13 @@ xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < NB; ++j) tma_load_3d(stg + 2 * Cfg::A_BYTES + j * SLAB, &mapHmn, &bars.full[s], 32 * j, t0, b);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, KP, 1, 1);
-            uint32_t acc = 0;
-            for (int i = 0; i < nk; ++i) {
+        const uint32_t idesc = make_idesc_tf32(TC_M, KP, 1, 1);
+        uint32_t acc = 0;
+        for (int i = 0; i < nk; ++i) {
+            if (lane == 0) {
                 const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
                 mbar_wait(&bars.conv[s], ph);
                 tcgen05_fence_after();
@@ -272,14 +340,16 @@ xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant_
                     mma_tf32_ss(tmem, dal, dbr, idesc, 1);
                 }
                 mma_commit(&bars.empty[s]);
+                if (i == nk - 1) mma_commit(&bars.accum);
             }
-            mma_commit(&bars.accum);
+            __syncwarp();
         }
-    } else if (warp >= 4) {
-        const int ct = threadIdx.x - 128;
+    } else {
+        const int ct = threadIdx.x - 64;
         for (int i = 0; i < nk; ++i) {
             const int s = i % Cfg::NSTAGE, ph = (i / Cfg::NSTAGE) & 1;
-            mbar_wait(&bars.full[s], ph);
+            if (lane == 0) mbar_wait(&bars.full[s], ph);
+            __syncwarp();
             float* raw = reinterpret_cast<float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
             write_lo(raw, raw + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
             write_lo(raw + 2 * Cfg::A_BYTES / 4, raw + (2 * Cfg::A_BYTES + Cfg::B_BYTES) / 4, Cfg::B_BYTES / 16, ct, TC_CONV_THREADS);
@@ -288,9 +358,11 @@ xht_tc_kernel(const __grid_constant__ CUtensorMap mapXmn, const __grid_constant_
         }
     }
     // ---- epilogue: rows of the accumulator straight to the partial buffers -------------------------------
-    if (nk > 0) mbar_wait(&bars.accum, 0);
-    tcgen05_fence_after();
+    __syncthreads();                                               // idle lanes park here
     if (warp >= 4) {
+        if (nk > 0 && lane == 0) mbar_wait(&bars.accum, 0);
+        __syncwarp();
+        tcgen05_fence_after();
         const int q = warp & 3;
         const int vcol = 128 * mt + q * 32 + lane;                 // virtual column = output row
         float* dst = nullptr;
@@ -367,7 +439,7 @@ static inline const CUtensorMap& as_map(const TcMapBlob& b) { return *reinterpre
 static inline CUtensorMap* as_map_ptr(TcMapBlob* b) { return reinterpret_cast<CUtensorMap*>(b); }
 template <int KP>
 static cudaError_t tc_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
-    using Cfg = TcCfg<KP>;
+    using Cfg = TcCfg<KP, XhtStages<KP>::value>;
     cudaError_t e = cudaFuncSetAttribute(xht_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     const int S = wk.tc_splits;
@@ -385,15 +457,35 @@ cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s)
 
 template <int KP>
 static cudaError_t tc_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
-    using Cfg = TcCfg<KP>;
+    using Cfg = TcCfg<KP, HStepStages<KP>::value>;
     const int ldw = p.ldf;
     AINMF_LAUNCH(wt_split_kernel, dim3(ceil_div(ldw, 32), KP / 32, p.B), dim3(kThreads), 0, s, p.W, p.w_stride, p.F, KP, ldw,
                  wk.tc_Wt, wk.tc_WtLo, (long long)KP * ldw, p.state);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(h_step_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
+    static long long* dbg = nullptr;
+    static int dbg_left = -1;
+    if (dbg_left < 0) {
+        const char* e_ = getenv("AINMF_TC_DEBUG");
+        dbg_left = (e_ && e_[0] == '1') ? 3 : 0;
+        if (dbg_left) { cudaMalloc((void**)&dbg, 4096 * sizeof(long long)); cudaMemset(dbg, 0, 4096 * sizeof(long long)); }
+    }
     AINMF_LAUNCH(h_step_tc_kernel<KP>, dim3(ceil_div(p.T, TC_M), p.B), dim3(kThreads), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX),
-                 as_map(wk.tc->mapWt), as_map(wk.tc->mapWtLo), p.F, p.T, wk.WtW, p.Ht, p.h_stride, wk.violH, p.state);
+                 as_map(wk.tc->mapWt), as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), p.F, p.T, wk.WtW,
+                 p.Ht, p.h_stride, wk.violH, p.state,
+                 dbg_left > 0 ? dbg : nullptr);
+    if (dbg_left > 0) {
+        --dbg_left;
+        long long hbuf[8 + 6 * 40];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hbuf, dbg, sizeof hbuf, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tc-debug h_step KP=%d] roles done %lld, accum %lld, epilogue %lld, end %lld cycles\n", KP, hbuf[0], hbuf[1], hbuf[2], hbuf[3]);
+        const int nk = (p.F + 31) / 32 + KP / 32;
+        for (int i = 0; i < nk && i < 40; ++i)
+            fprintf(stderr, "  stage %2d: slot free %7lld  tma issued %7lld  full seen %7lld  converted(t0) %7lld  conv barrier %7lld  mma committed %7lld\n", i,
+                    hbuf[8 + 6 * i + 5], hbuf[8 + 6 * i], hbuf[8 + 6 * i + 1], hbuf[8 + 6 * i + 2], hbuf[8 + 6 * i + 4], hbuf[8 + 6 * i + 3]);
+    }
     return cudaGetLastError();
 }
 cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
@@ -408,6 +500,8 @@ int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* m) {
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapWtLo), wk->tc_WtLo, F, KP, B, ldf, KP * ldf, TC_BK, (uint32_t)KP, 0);
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapXmn), p.Xt, F, T, B, ldf, (uint64_t)p.x_stride, 32, TC_BK, 1);
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapHmn), p.Ht, KP, T, B, KP, (uint64_t)p.h_stride, 32, TC_BK, 1);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapHk), p.Ht, KP, T, B, KP, (uint64_t)p.h_stride, TC_BK, TC_M, 0);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapG), wk->WtW, KP, KP, B, KP, KP * KP, TC_BK, (uint32_t)KP, 0);
     wk->tc = m;
     return rc;
 }

@@ -106,3 +106,28 @@ def test_emu_invalid_arguments():
         assert e.value.code == E.capi.ERR_INVALID, kw
     with pytest.raises(E.capi.AinmfError):
         E.stft(np.zeros(50, np.float32), 128, 32)
+
+
+@pytest.mark.parametrize("KP,rows", [(32, 200), (64, 130), (128, 257)])
+def test_emu_incremental_sweep_matches_reference_sweep(KP, rows):
+    """cd_sweep_rows_inc (the sweep of the tensor-core h-step) against the reference sweep order of
+    _cdnmf_fast.pyx, on random non-negative factors with some exact zeros."""
+    import ctypes as C
+    rng = np.random.default_rng(KP)
+    A = np.abs(rng.standard_normal((rows, KP))).astype(np.float32)
+    A[rng.random((rows, KP)) < 0.2] = 0
+    Hm = np.abs(rng.standard_normal((KP + 40, KP))).astype(np.float32)
+    G = (Hm.T @ Hm).astype(np.float32)
+    G[:, 5] = 0; G[5, :] = 0                                   # a dead component: zero Gram diagonal -> skipped
+    Bm = (np.abs(rng.standard_normal((rows, KP))) * KP).astype(np.float32)
+    want = A.copy()
+    v_want = restate.cd_sweep(want, G, Bm)
+    got = A.copy()
+    viol = np.zeros((rows + 127) // 128, np.float32)
+    fn = E.lib().ainmf_test_sweep_inc
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert fn(E.ptr(got), E.ptr(G), E.ptr(Bm), rows, KP, E.ptr(viol), None) == 0
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 2e-4 * scale
+    assert abs(viol.sum() - v_want) < 1e-3 * v_want
