@@ -252,7 +252,7 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     if (p->rank < 1 || p->rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", p->rank);
     if (p->max_iter < 1) return fail(h, AINMF_ERR_INVALID, "max_iter must be >= 1");
     if (!(p->tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "tol must be >= 0");
-    if (p->solver != AINMF_SOLVER_CD) return fail(h, AINMF_ERR_INVALID, "solver %d is not available in this build (CD only)", p->solver);
+    if (p->solver != AINMF_SOLVER_CD && p->solver != AINMF_SOLVER_MU) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu)", p->solver);
     if (p->n_outer < 1) return fail(h, AINMF_ERR_INVALID, "n_outer must be >= 1");
     if (geometry(p->n_samples, p->n_fft, p->hop, &pl->g)) return fail(h, AINMF_ERR_INVALID, "signal too long");
     if (p->col_start >= 0) {
@@ -267,6 +267,7 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     const int KP = pl->KP;
     impute_plan(T, &pl->iw);
     nmf_plan(B, T, F, KP, h->n_sm, &pl->nw);
+    if (p->solver == AINMF_SOLVER_MU) { pl->nw.want_mu = 1; pl->nw.use_tc = 0; }
     pl->vz_stride = (long long)T * ldf;
     pl->bad_stride = round_up(T, 16);
     pl->w_stride = (long long)F * KP;
@@ -318,9 +319,12 @@ __global__ void status_summary_kernel(const ClipState* st, int B, int* out) {
 // Runs up to max_iter iterations, polling the stop flags every `poll` iterations when tol > 0.
 int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, int max_iter, float tol, int* d_flag,
                    cudaStream_t s) {
-    const int poll = 8;
+    const bool mu = prob.solver == AINMF_SOLVER_MU;
+    const int poll = mu ? 10 : 8;          // MU tests convergence every 10th iteration only
+    if (mu && tol > 0.f) CU(h, nmf_mu_begin(prob, nw, s));
     for (int it = 1; it <= max_iter; ++it) {
-        CU(h, nmf_cd_iterate(prob, nw, it, s));
+        if (mu) CU(h, nmf_mu_iterate(prob, nw, it, s));
+        else CU(h, nmf_cd_iterate(prob, nw, it, s));
         if (tol > 0.f && (it % poll == 0) && it < max_iter) {
             AINMF_LAUNCH(count_not_done_kernel, dim3(1), dim3(kThreads), 0, s, prob.state, prob.B, d_flag);
             CU(h, cudaGetLastError());
@@ -453,7 +457,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     if (!X_ft || batch <= 0 || F < 1 || T < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_nmf_fit");
     if (rank < 1 || rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", rank);
     if (max_iter < 1 || !(tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "need max_iter >= 1 and tol >= 0");
-    if (solver != AINMF_SOLVER_CD) return fail(h, AINMF_ERR_INVALID, "solver %d is not available in this build (CD only)", solver);
+    if (solver != AINMF_SOLVER_CD && solver != AINMF_SOLVER_MU) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu)", solver);
     if ((W0 == nullptr) != (H0 == nullptr)) return fail(h, AINMF_ERR_INVALID, "W0 and H0 must be given together");
     cudaStream_t s = (cudaStream_t)stream;
     CU(h, cudaSetDevice(h->device));
@@ -462,6 +466,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     NmfWork nw;
     impute_plan(T, &iw);
     nmf_plan(B, T, F, KP, h->n_sm, &nw);
+    if (solver == AINMF_SOLVER_MU) { nw.want_mu = 1; nw.use_tc = 0; }
     const long long xs = (long long)T * ldf, ws = (long long)F * KP, hs = (long long)T * KP;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
@@ -473,7 +478,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     if (rc) return rc;
     char* base = (char*)scr;
     NmfProblem pr;
-    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = tol;
+    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = tol; pr.solver = solver;
     pr.Xt = (float*)(base + oX); pr.x_stride = xs;
     pr.W = (float*)(base + oW); pr.w_stride = ws;
     pr.Ht = (float*)(base + oH); pr.h_stride = hs;
@@ -483,6 +488,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     unsigned char* nobad = (unsigned char*)(base + oB);
     TcMaps tcm;
     if (nmf_tc_setup(pr, &nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (nw.zero_flags) CU(h, cudaMemsetAsync(nw.zero_flags, 0, (size_t)B * nw.zero_stride, s));
     CU(h, cudaMemsetAsync(nw.counters, 0, sizeof(unsigned) * B, s));
     CU(h, cudaMemsetAsync(nobad, 0, (size_t)B * round_up(T, 16), s));
     CU(h, cudaMemsetAsync(pr.state, 0, sizeof(ClipState) * B, s));
@@ -576,13 +582,14 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     impute_carve(base + pl.off_imp, B, F, &pl.iw);
     nmf_carve(base + pl.off_nmf, B, T, F, KP, &pl.nw);
     NmfProblem pr;
-    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = p->tol;
+    pr.B = B; pr.T = T; pr.F = F; pr.ldf = ldf; pr.KP = KP; pr.tol = p->tol; pr.solver = p->solver;
     pr.Xt = V; pr.x_stride = pl.vz_stride;
     pr.W = (float*)(base + pl.off_W); pr.w_stride = pl.w_stride;
     pr.Ht = (float*)(base + pl.off_Ht); pr.h_stride = pl.h_stride;
     pr.state = st;
     TcMaps tcm;
     if (nmf_tc_setup(pr, &pl.nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (pl.nw.zero_flags) CU(h, cudaMemsetAsync(pl.nw.zero_flags, 0, (size_t)B * pl.nw.zero_stride, s));
 
     CU(h, cudaMemsetAsync(pl.nw.counters, 0, sizeof(unsigned) * B, s));
     // a4: STFT

@@ -71,6 +71,8 @@ struct ClipState {
     double sum_x;        // sum of the imputed spectrogram (for the init scale)
     float mean_x;        // mean of the imputed spectrogram
     float err;           // ||X - W H||_F
+    double err_init;     // MU solver: error of the initial factors and of the previous check (sklearn tests
+    double err_prev;     //            (previous_error - error) / error_at_init < tol every 10 iterations)
 };
 
 // ---- impute.cu ----------------------------------------------------------------------------------
@@ -120,6 +122,7 @@ void prof_collect(double* ms /*[PROF_KINDS]*/, long long* counts /*[PROF_KINDS]*
 // ---- nmf_cd.cu ----------------------------------------------------------------------------------
 struct NmfProblem {
     int B, T, F, ldf, KP;
+    int solver = 0;                     // 0 = coordinate descent (the reference's), 1 = multiplicative update (Frobenius)
     float tol;
     float* Xt; long long x_stride;      // [B][T][ldf]
     float* W; long long w_stride;       // [B][F][KP]
@@ -143,6 +146,11 @@ struct NmfWork {
     // time-frame-sharded mode only (B == 1); null otherwise
     float* xht_reduced = nullptr;       // [F][KP]: local X.Ht summed over the splits = first part of the all-reduce buffer
     double* h_viol_sum = nullptr;       // [B]: local H-side violation, all-reduced by the caller before the stop rule
+    // multiplicative-update solver
+    float* xtw = nullptr;               // [B][T][KP]: X^T.W (the MU numerator of the H update)
+    unsigned char* zero_flags = nullptr;  // [B][zero_stride] zeros: error evaluation that must not overwrite frames
+    long long zero_stride = 0;
+    int want_mu = 0;                    // set before nmf_work_bytes / nmf_carve when solver == MU
 };
 enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4 };
 void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
@@ -153,6 +161,11 @@ cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s)
 cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // Wt split, X^T.W + H sweep
 void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
+// multiplicative update, Frobenius loss (sklearn solver='mu': $SP/sklearn/decomposition/_nmf.py:536-549,615-624,
+// 633-635,701-721,867-879).  nmf_mu_begin evaluates the error of the initial factors; nmf_mu_iterate does one
+// W and H update and, every 10th iteration when tol > 0, the convergence test.
+cudaError_t nmf_mu_begin(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);
+cudaError_t nmf_mu_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
 // the same iteration in pieces, so that a collective can be placed between them (time-sharded mode):
 // PARTIALS: HHt and X.Ht of the local frames; UPDATE: W sweep, WtW, fused X^T.W + H sweep; STOP: the stop rule
 cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kThreads)
 h_step_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int T,
               const float* __restrict__ W, long long w_stride, const float* __restrict__ G,
               float* __restrict__ Ht, long long h_stride, float* __restrict__ viol /*[B][gridDim.x]*/,
-              const ClipState* __restrict__ st) {
+              const ClipState* __restrict__ st, float* __restrict__ xtw_out /*MU solver: store X^T.W, no sweep*/) {
     using Cfg = HStepCfg<KP, BM>;
     constexpr int TN = KP / 16, TM = BM / 16, L = Cfg::L, SL = KP / L, BK = Cfg::BK;
     constexpr int APITCH = Cfg::APITCH, CPITCH = Cfg::CPITCH;
@@ -395,6 +395,14 @@ h_step_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, 
 #pragma unroll
         for (int j = 0; j < TN; ++j) sC[(ty + 16 * i) * CPITCH + frag_col<TN>(tx, j)] = acc[i][j];
     __syncthreads();
+    if (xtw_out) {      // whole block: the multiplicative-update solver wants the plain product
+        float* ob = xtw_out + (long long)b * h_stride;
+        for (int i = threadIdx.x; i < BM * KP / 4; i += blockDim.x) {
+            const int r = (4 * i) / KP, c = (4 * i) % KP;
+            if (m0 + r < T) *reinterpret_cast<float4*>(ob + (long long)(m0 + r) * KP + c) = *reinterpret_cast<const float4*>(sC + r * CPITCH + c);
+        }
+        return;
+    }
 
     constexpr int ROWS = kThreads / L;                      // rows swept per pass
     const int l = threadIdx.x % L;
@@ -553,14 +561,14 @@ static cudaError_t run_gram(const float* A, long long a_stride, int rows, int B,
 }
 
 template <int KP, int BM>
-static cudaError_t run_h_step(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+static cudaError_t run_h_step(const NmfProblem& p, const NmfWork& wk, cudaStream_t s, float* xtw_out = nullptr) {
     using Cfg = HStepCfg<KP, BM>;
     cudaError_t e = cudaFuncSetAttribute(h_step_kernel<KP, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return e;
     auto kern = h_step_kernel<KP, BM>;
     AINMF_LAUNCH(kern, dim3(ceil_div(p.T, BM), p.B), dim3(kThreads), Cfg::smem_bytes, s, p.Xt,
-                 p.x_stride, p.ldf, p.F, p.T, p.W, p.w_stride, wk.WtW, p.Ht, p.h_stride, wk.violH, p.state);
+                 p.x_stride, p.ldf, p.F, p.T, p.W, p.w_stride, wk.WtW, p.Ht, p.h_stride, wk.violH, p.state, xtw_out);
     return cudaGetLastError();
 }
 
@@ -687,6 +695,157 @@ static cudaError_t finalize_impl(const NmfProblem& p, const NmfWork& wk, const u
     return cudaGetLastError();
 }
 
+// =====================================================================================================
+// multiplicative update (Frobenius):  A[row,:] *= Num[row,:] / (A[row,:] . G), zero denominators -> float32 eps
+// ($SP/sklearn/decomposition/_nmf.py:536-549 for W, :615-624 for H).  Num = sum over `S` split buffers.
+// 32 rows per block, 8 lanes per row; grid = (ceil(rows/32), B).
+// =====================================================================================================
+template <int KP>
+__global__ void __launch_bounds__(kThreads)
+mu_rows_kernel(float* __restrict__ A, long long a_stride, int rows, const float* __restrict__ G,
+               const float* __restrict__ num, int S, long long num_split_stride, long long num_clip_stride,
+               const ClipState* __restrict__ st) {
+    constexpr int L = 8, SL = KP / L, PITCH = KP + 4 * L;
+    AINMF_DYN_SMEM(smem_raw);
+    float* sG = reinterpret_cast<float*>(smem_raw);        // [KP][PITCH] padded as in load_gram_padded<KP, 8>
+    float* sA = sG + KP * PITCH;                           // [32][KP]
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    load_gram_padded<KP, L>(sG, G + (long long)b * KP * KP);
+    const int l = threadIdx.x % L, lr = threadIdx.x / L;
+    const int row = blockIdx.x * 32 + lr;
+    const bool valid = row < rows;
+    float* ar = A + (long long)b * a_stride + (long long)row * KP;
+    for (int i = threadIdx.x; i < 32 * KP / 4; i += blockDim.x) {
+        const int r = (4 * i) / KP, c = (4 * i) % KP;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (blockIdx.x * 32 + r < rows) v = *reinterpret_cast<const float4*>(A + (long long)b * a_stride + (long long)(blockIdx.x * 32 + r) * KP + c);
+        *reinterpret_cast<float4*>(sA + r * KP + c) = v;
+    }
+    __syncthreads();
+    float den[SL];
+#pragma unroll
+    for (int q = 0; q < SL; ++q) den[q] = 0.f;
+    const float* arow = sA + lr * KP;
+    const float* gl = sG + l * (SL + 4);
+    for (int r = 0; r < KP; ++r) {
+        const float a = arow[r];
+        const float* g = gl + r * PITCH;                   // G[r][l*SL .. ] (G symmetric: column slice = row slice)
+#pragma unroll
+        for (int q = 0; q < SL; q += 4) {
+            const float4 gv = *reinterpret_cast<const float4*>(g + q);
+            den[q] = fmaf(a, gv.x, den[q]);
+            den[q + 1] = fmaf(a, gv.y, den[q + 1]);
+            den[q + 2] = fmaf(a, gv.z, den[q + 2]);
+            den[q + 3] = fmaf(a, gv.w, den[q + 3]);
+        }
+    }
+    if (valid) {
+        float nm[SL];
+#pragma unroll
+        for (int q = 0; q < SL; ++q) nm[q] = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const float* nr = num + (long long)b * num_clip_stride + (long long)s * num_split_stride + (long long)row * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(nr + q);
+                nm[q] += v.x; nm[q + 1] += v.y; nm[q + 2] += v.z; nm[q + 3] += v.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SL; q += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = (den[q + e] == 0.f) ? 1.1920929e-07f : den[q + e];
+                o[e] = arow[l * SL + q + e] * (nm[q + e] / d);
+            }
+            *reinterpret_cast<float4*>(ar + l * SL + q) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// it == 0: error of the initial factors; it % 10 == 0: (previous_error - error) / error_at_init < tol ($SP .../_nmf.py:867-879)
+__global__ void __launch_bounds__(kThreads)
+mu_stop_kernel(ClipState* __restrict__ st, int B, int it, float tol) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ClipState s = st[b];
+    if (s.done) return;
+    const double e = (double)s.err;
+    if (it == 0) { s.err_init = e; s.err_prev = e; }
+    else {
+        if ((s.err_prev - e) / s.err_init < (double)tol) s.done = 1;
+        s.err_prev = e;
+    }
+    st[b] = s;
+}
+__global__ void __launch_bounds__(kThreads)
+mu_tick_kernel(ClipState* __restrict__ st, int B, int it) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && !st[b].done) st[b].n_iter = it;
+}
+
+template <int KP>
+static cudaError_t mu_rows(float* A, long long a_stride, int rows, const float* G, const float* num, int S,
+                           long long num_split_stride, long long num_clip_stride, const NmfProblem& p, cudaStream_t s) {
+    const size_t smem = sizeof(float) * ((size_t)KP * (KP + 32) + 32 * KP);
+    cudaError_t e = cudaFuncSetAttribute(mu_rows_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    AINMF_LAUNCH(mu_rows_kernel<KP>, dim3(ceil_div(rows, 32), p.B), dim3(kThreads), smem, s, A, a_stride, rows, G, num, S,
+                 num_split_stride, num_clip_stride, p.state);
+    return cudaGetLastError();
+}
+
+template <int KP>
+static cudaError_t mu_error(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    cudaError_t e = finalize_impl<KP>(p, wk, wk.zero_flags, wk.zero_stride, nullptr, s);
+    if (e != cudaSuccess) return e;
+    AINMF_LAUNCH(mu_stop_kernel, dim3(ceil_div(p.B, kThreads)), dim3(kThreads), 0, s, p.state, p.B, it, p.tol);
+    return cudaGetLastError();
+}
+
+template <int KP>
+static cudaError_t mu_iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    cudaError_t e;
+    const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
+    const int S = ceil_div(p.T, fps);
+    // W <- W * (X Ht) / (W (Ht^T Ht))
+    if ((e = run_gram<KP>(p.Ht, p.h_stride, p.T, p.B, wk, wk.HHt, p.state, s)) != cudaSuccess) return e;
+    AINMF_LAUNCH(xht_kernel<KP>, dim3(ceil_div(p.F, 128), S, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf, p.F, p.T,
+                 p.Ht, p.h_stride, fps, wk.xht_partial, p.state);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = mu_rows<KP>(p.W, p.w_stride, p.F, wk.HHt, wk.xht_partial, S, (long long)p.F * KP, (long long)S * p.F * KP, p, s)) != cudaSuccess) return e;
+    // H <- H * (W^T X) / ((W^T W) H)
+    if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
+    if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s, wk.xtw);
+    else if (wk.h_bm == 64) e = run_h_step<KP, 64>(p, wk, s, wk.xtw);
+    else e = run_h_step<KP, 128>(p, wk, s, wk.xtw);
+    if (e != cudaSuccess) return e;
+    if ((e = mu_rows<KP>(p.Ht, p.h_stride, p.T, wk.WtW, wk.xtw, 1, 0, p.h_stride, p, s)) != cudaSuccess) return e;
+    AINMF_LAUNCH(mu_tick_kernel, dim3(ceil_div(p.B, kThreads)), dim3(kThreads), 0, s, p.state, p.B, it);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (p.tol > 0.f && it % 10 == 0) return mu_error<KP>(p, wk, it, s);
+    return cudaSuccess;
+}
+
+cudaError_t nmf_mu_begin(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    switch (p.KP) {
+        case 32: return mu_error<32>(p, wk, 0, s);
+        case 64: return mu_error<64>(p, wk, 0, s);
+        case 128: return mu_error<128>(p, wk, 0, s);
+    }
+    return (cudaError_t)1;
+}
+cudaError_t nmf_mu_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s) {
+    switch (p.KP) {
+        case 32: return mu_iterate_impl<32>(p, wk, it, s);
+        case 64: return mu_iterate_impl<64>(p, wk, it, s);
+        case 128: return mu_iterate_impl<128>(p, wk, it, s);
+    }
+    return (cudaError_t)1;
+}
+
 cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
                          cudaStream_t s, double* err_sq) {
     switch (p.KP) {
@@ -747,6 +906,7 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
     if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)); // Wt, Wt_lo
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
+    if (wk.want_mu) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
     return n;
 }
 
@@ -767,6 +927,11 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);
     wk->err_partial = (double*)take(sizeof(double) * (size_t)B * ceil_div(T, 16));
+    if (wk->want_mu) {
+        wk->xtw = (float*)take(sizeof(float) * (size_t)B * T * KP);
+        wk->zero_stride = round_up(T, 16);
+        wk->zero_flags = (unsigned char*)take((size_t)B * wk->zero_stride);      // the caller zeroes it once
+    }
 }
 
 #ifdef AINMF_EMU

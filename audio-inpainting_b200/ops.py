@@ -18,12 +18,12 @@ _LIBRARY = torch.library.Library("ainmf", "DEF")
 _LIBRARY.define("stft(Tensor x, int n_fft, int hop) -> (Tensor, Tensor)")
 _LIBRARY.define("gap_mask(Tensor x, int hop, int n_frames, float threshold, int frac_num, int frac_den) "
                 "-> (Tensor, Tensor, Tensor)")
-_LIBRARY.define("nmf_fit(Tensor X, int rank, int max_iter, float tol, int seed, Tensor? W0, Tensor? H0) "
-                "-> (Tensor, Tensor, Tensor, Tensor)")
+_LIBRARY.define("nmf_fit(Tensor X, int rank, int max_iter, float tol, int seed, Tensor? W0, Tensor? H0, "
+                "str solver='cd') -> (Tensor, Tensor, Tensor, Tensor)")
 _LIBRARY.define("istft(Tensor Z, int n_fft, int hop, int length) -> Tensor")
 _LIBRARY.define("nmf_inpaint(Tensor x, int n_fft, int hop, int rank, int max_iter, float tol, int seed, "
                 "float threshold, int frac_num, int frac_den, int col_start, int col_end, int n_outer, "
-                "Tensor? W0, Tensor? H0) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+                "Tensor? W0, Tensor? H0, str solver='cd') -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
 _LIBRARY.define("load_pcm16(Tensor pcm) -> (Tensor, Tensor)")
 _LIBRARY.define("store_pcm16(Tensor y) -> Tensor")
 
@@ -79,7 +79,15 @@ def _gap_mask(x, hop, n_frames, threshold, frac_num, frac_den):
     return bad, idx, nb
 
 
-def _nmf_fit(X, rank, max_iter, tol, seed, W0, H0):
+def _solver_id(solver: str) -> int:
+    try:
+        return {"cd": _capi.SOLVER_CD, "mu": _capi.SOLVER_MU}[solver]
+    except KeyError:
+        raise RuntimeError(f"unknown solver {solver!r}: 'cd' (sklearn coordinate descent, what the reference runs) or "
+                           "'mu' (multiplicative update, Frobenius)") from None
+
+
+def _nmf_fit(X, rank, max_iter, tol, seed, W0, H0, solver="cd"):
     X = _f32(X, "X")
     if X.dim() != 3:
         raise RuntimeError("X must be [B, F, T]")
@@ -96,7 +104,7 @@ def _nmf_fit(X, rank, max_iter, tol, seed, W0, H0):
         H = torch.empty((B, rank, T), dtype=torch.float32, device=X.device)
         err = torch.empty((B,), dtype=torch.float32, device=X.device)
         nit = torch.empty((B,), dtype=torch.int32, device=X.device)
-        _lib.check(L.ainmf_nmf_fit(_lib.handle(dev), _p(X), B, F, T, rank, max_iter, tol, _capi.SOLVER_CD,
+        _lib.check(L.ainmf_nmf_fit(_lib.handle(dev), _p(X), B, F, T, rank, max_iter, tol, _solver_id(solver),
                                    seed & 0xFFFFFFFF, _p(W0), _p(H0), _p(W), _p(H), _p(err), _p(nit),
                                    _stream(dev)), dev)
     return W, H, err, nit
@@ -130,7 +138,7 @@ def _workspace(dev: int, nbytes: int) -> torch.Tensor:
 
 
 def _nmf_inpaint(x, n_fft, hop, rank, max_iter, tol, seed, threshold, frac_num, frac_den, col_start, col_end,
-                 n_outer, W0, H0):
+                 n_outer, W0, H0, solver="cd"):
     x = _f32(x, "x")
     if x.dim() != 2:
         raise RuntimeError("x must be [B, N]")
@@ -141,7 +149,7 @@ def _nmf_inpaint(x, n_fft, hop, rank, max_iter, tol, seed, threshold, frac_num, 
         h = _lib.handle(dev)
         p = _capi.default_params(L, batch=B, n_samples=N, n_fft=n_fft, hop=hop, rank=rank, max_iter=max_iter, tol=tol,
                                  seed=seed & 0xFFFFFFFF, threshold=threshold, frac_num=frac_num, frac_den=frac_den,
-                                 col_start=col_start, col_end=col_end, n_outer=n_outer)
+                                 col_start=col_start, col_end=col_end, n_outer=n_outer, solver=_solver_id(solver))
         nbytes = L.ainmf_workspace_bytes(h, C.byref(p))
         if nbytes == 0:
             _lib.check(_capi.ERR_INVALID, dev)

@@ -89,7 +89,7 @@ def gap_mask(x, hop, T, thr, num, den):
     return bad, idx, nb
 
 
-def nmf_fit(X, K, max_iter=200, tol=1e-4, seed=0, W0=None, H0=None):
+def nmf_fit(X, K, max_iter=200, tol=1e-4, seed=0, W0=None, H0=None, solver=0):
     X = np.ascontiguousarray(X, np.float32)
     if X.ndim == 2:
         X = X[None]
@@ -101,7 +101,7 @@ def nmf_fit(X, K, max_iter=200, tol=1e-4, seed=0, W0=None, H0=None):
     if W0 is not None:
         W0 = np.ascontiguousarray(np.broadcast_to(W0, (B, F, K)), np.float32)
         H0 = np.ascontiguousarray(np.broadcast_to(H0, (B, K, T)), np.float32)
-    check(lib().ainmf_nmf_fit(handle(), ptr(X), B, F, T, K, max_iter, tol, capi.SOLVER_CD, seed, ptr(W0), ptr(H0),
+    check(lib().ainmf_nmf_fit(handle(), ptr(X), B, F, T, K, max_iter, tol, solver, seed, ptr(W0), ptr(H0),
                               ptr(W), ptr(H), ptr(err), ptr(nit), None))
     return W, H, err, nit
 

@@ -87,10 +87,10 @@ def test_emu_part0_variant():
     t = np.arange(N) / sr
     raw = (0.6 * np.sin(2 * np.pi * 300 * t) + 0.2 * np.sin(2 * np.pi * 900 * t) + 0.02 * rng.standard_normal(N)).astype(np.float32)
     cor, gs, ge = libcalls.part0_apply_mask(raw, 0.2)
-    yo, so = libcalls.part0_restore(raw, cor, sr, gs, ge, n_fft=n_fft, hop=hop, K=K, n_outer=3, seed=0,
-                                    max_iter=25, return_all=True)
+    yo, so = libcalls.part0_restore(raw, cor, sr, gs, ge, n_fft=n_fft, hop=hop, K=K, n_outer=2, seed=0,
+                                    max_iter=12, return_all=True)
     cs, ce = so["cols"]
-    r = E.inpaint(cor, n_fft=n_fft, hop=hop, rank=K, max_iter=25, tol=1e-4, seed=0, col_start=cs, col_end=ce, n_outer=3)
+    r = E.inpaint(cor, n_fft=n_fft, hop=hop, rank=K, max_iter=12, tol=1e-4, seed=0, col_start=cs, col_end=ce, n_outer=2)
     assert abs(int(r["n_iter"][0]) - so["n_iters"][-1]) <= 1
     assert libcalls.snr_db(so["pre_blend"], r["y"][0]) > 60
 
@@ -98,7 +98,7 @@ def test_emu_part0_variant():
 def test_emu_invalid_arguments():
     x = np.zeros(4000, np.float32)
     for kw in (dict(n_fft=100, hop=25), dict(n_fft=128, hop=48), dict(rank=0), dict(rank=129), dict(max_iter=0),
-               dict(n_fft=8192, hop=2048), dict(col_start=0, col_end=3), dict(n_outer=0), dict(solver=1)):
+               dict(n_fft=8192, hop=2048), dict(col_start=0, col_end=3), dict(n_outer=0), dict(solver=7)):
         p = dict(n_fft=128, hop=32, rank=8, max_iter=2)
         p.update(kw)
         with pytest.raises(E.capi.AinmfError) as e:
@@ -131,3 +131,17 @@ def test_emu_incremental_sweep_matches_reference_sweep(KP, rows):
     scale = np.abs(want).max()
     assert np.abs(got - want).max() < 2e-4 * scale
     assert abs(viol.sum() - v_want) < 1e-3 * v_want
+
+
+@pytest.mark.parametrize("F,T,K,iters,tol", [(65, 95, 8, 12, 0.0), (40, 60, 6, 30, 1e-3)])
+def test_emu_mu_solver_matches_sklearn_mu(F, T, K, iters, tol):
+    """solver='mu' (Frobenius multiplicative update) against sklearn's, same initial factors; with tol > 0 the
+    every-10-iterations stop test must fire at the same iteration."""
+    rng = np.random.default_rng(F + K)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    W0, Ht0 = restate.init_factors(X.mean(), F, T, K, 3)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, W0=W0, H0=Ht0.T, max_iter=iters, tol=tol, solver="mu")
+    W, H, err, nit = E.nmf_fit(X, K, max_iter=iters, tol=tol, W0=W0, H0=np.ascontiguousarray(Ht0.T), solver=E.capi.SOLVER_MU)
+    assert nit[0] == no
+    assert abs(err[0] - eo) < 1e-4 * eo
+    assert rel_l2(W[0], Wo) < 1e-3 and rel_l2(H[0], Ho) < 1e-3

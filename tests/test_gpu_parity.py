@@ -309,3 +309,30 @@ def test_shim_classes_match_reference_interface(ops, golden, tmp_path):
     m = ainmf.NMFFairInpainter(str(path))
     m.load_damaged_data()
     assert np.array_equal(m.get_mask_from_signal(1724, 256), libcalls.column_mask(m.signal, 1724, 256, 0.01, 0.8))
+
+
+@pytest.mark.parametrize("F,T,K,iters,tol", [(513, 300, 64, 30, 0.0), (257, 400, 40, 60, 1e-3), (129, 200, 16, 20, 0.0)])
+def test_mu_solver_matches_sklearn_mu(ops, F, T, K, iters, tol):
+    """solver='mu' (Frobenius multiplicative update, the north-star-shaped solver) vs sklearn solver='mu'."""
+    rng = np.random.default_rng(F + K)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    W0, Ht0 = restate.init_factors(X.mean(), F, T, K, 3)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, W0=W0, H0=Ht0.T, max_iter=iters, tol=tol, solver="mu")
+    W, H, err, nit = ops.nmf_fit(dev(X[None]), K, iters, tol, 0, dev(W0[None]), dev(np.ascontiguousarray(Ht0.T)[None]), "mu")
+    assert int(nit[0]) == no
+    assert abs(float(err[0]) - eo) <= 1e-4 * eo
+    assert rel_l2(W[0].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 1e-3
+
+
+def test_ffma_path_still_matches_when_tensor_cores_disabled(ops, golden):
+    """AINMF_DISABLE_TC=1 routes K >= 64 problems through the FFMA kernels; both paths must satisfy the same gates."""
+    import os
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); import ainmf; from oracle import libcalls; "
+            "rng = np.random.default_rng(1); X = np.abs(rng.standard_normal((513, 300))).astype(np.float32); "
+            "Wo, Ho, no, eo = libcalls.nmf_fit(X, 64, seed=0, max_iter=15, tol=0.0); "
+            "W, H, err, nit = ainmf.ops.nmf_fit(torch.from_numpy(X[None]).cuda(), 64, 15, 0.0, 0, None, None); "
+            "assert abs(float(err[0]) - eo) <= 1e-4 * eo, (float(err[0]), eo); print('FFMA_OK')") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, AINMF_DISABLE_TC="1"), capture_output=True, text=True, timeout=300)
+    assert "FFMA_OK" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
