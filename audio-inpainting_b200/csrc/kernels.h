@@ -131,13 +131,14 @@ struct NmfProblem {
 };
 // TMA tensor maps of the tensor-core path (each an opaque 128-byte CUtensorMap; built on the host per problem)
 struct alignas(64) TcMapBlob { unsigned char b[128]; };
-struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn, mapHk, mapG; };
+struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn, mapHk, mapG, mapGlo; };
 
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;
     // tensor-core path (tcgen05, error-compensated TF32) for the two V-sized contractions; KP in {64,128}
     int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
     float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed, and its TF32 residual
+    float* tc_GLo = nullptr;                      // [B][KP][KP]: TF32 residual of W^T W
     const TcMaps* tc = nullptr;
     float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
     float *violW = nullptr, *violH = nullptr;

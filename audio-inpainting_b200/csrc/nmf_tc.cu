@@ -34,7 +34,9 @@ template <int KP, int NSTAGE_> struct TcCfg {
     static constexpr int L = 8, R = 4;                             // sweep: 8 lanes x 4 frames per group, one pass
     static constexpr int CPITCH = KP + 4;
     static constexpr int GPITCH = KP + 4 * L;
-    static constexpr int EPI_BYTES = (TC_M * CPITCH + KP * GPITCH + KP) * 4;
+    static constexpr int EPI_SHFL_BYTES = (TC_M * CPITCH + KP * GPITCH + KP) * 4;
+    static constexpr int EPI_BLK_BYTES = (2 * KP * KP + 2 * TC_M * 8 + KP) * 4;     // G, G_lo (swizzled), delta hi/lo, 1/diag
+    static constexpr int EPI_BYTES = EPI_SHFL_BYTES > EPI_BLK_BYTES ? EPI_SHFL_BYTES : EPI_BLK_BYTES;
     static constexpr int PIPE_BYTES = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + 1024;   // + alignment slack
 };
@@ -43,6 +45,7 @@ template <int KP> struct XhtStages { static constexpr int value = (KP == 64) ? 4
 
 struct TcBarriers {
     uint64_t full[4], conv[4], empty[4], accum;
+    uint64_t gload, dready, ddone;      // blocked sweep: Gram tiles landed / delta tile written / rank-8 update done
 };
 
 // a_lo = a - trunc_tf32(a) for `n4` float4 of a tile; the raw tile is left in place as a_hi.  Loads are issued in
@@ -79,11 +82,12 @@ __device__ __forceinline__ void write_lo(const float* __restrict__ raw, float* _
 //   stages nkX .. nkX+KP/32: A = Ht chunk (K-major), B = W^T W chunk; both lo tiles by the converters; A negated
 // Stage layout: [A raw][A lo][B raw][B lo].
 // =====================================================================================================
-template <int KP>
+template <int KP, bool BLK>
 __global__ void __launch_bounds__(kThreads, (KP == 64) ? 2 : 1)
 h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWt,
                  const __grid_constant__ CUtensorMap mapWtLo, const __grid_constant__ CUtensorMap mapHk,
-                 const __grid_constant__ CUtensorMap mapG, int F, int T, const float* __restrict__ G,
+                 const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGlo, int F, int T,
+                 const float* __restrict__ G,
                  float* __restrict__ Ht, long long h_stride, float* __restrict__ viol, const ClipState* __restrict__ st,
                  long long* __restrict__ dbg) {
     using Cfg = TcCfg<KP, HStepStages<KP>::value>;
@@ -106,8 +110,10 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.conv[s], TC_CONV_THREADS); mbar_init(&bars.empty[s], 1); }
         mbar_init(&bars.accum, 1);
+        mbar_init(&bars.gload, 1); mbar_init(&bars.dready, 128); mbar_init(&bars.ddone, 1);
         mbar_fence_init();
         tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWt); tma_prefetch_desc(&mapWtLo); tma_prefetch_desc(&mapHk); tma_prefetch_desc(&mapG);
+        tma_prefetch_desc(&mapGlo);
     }
     if (warp == 1) tmem_alloc(&tmem_slot, KP);
     tcgen05_fence_before();
@@ -130,9 +136,10 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapWt, &bars.full[s], i * TC_BK, 0, b);
                     tma_load_3d(stg + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapWtLo, &bars.full[s], i * TC_BK, 0, b);
                 } else {
-                    mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                    mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
                     tma_load_3d(stg, &mapHk, &bars.full[s], (i - nkX) * TC_BK, m0, b);
                     tma_load_3d(stg + 2 * Cfg::A_BYTES, &mapG, &bars.full[s], (i - nkX) * TC_BK, 0, b);
+                    tma_load_3d(stg + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapGlo, &bars.full[s], (i - nkX) * TC_BK, 0, b);
                 }
                 DBG(8 + 6 * i + 0);
             }
@@ -178,13 +185,122 @@ h_step_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             if (ct == 0) DBG(8 + 6 * i + 1);
             float* raw = reinterpret_cast<float*>(smem + (size_t)s * Cfg::STAGE_BYTES);
             write_lo(raw, raw + Cfg::A_BYTES / 4, Cfg::A_BYTES / 16, ct, TC_CONV_THREADS);
-            if (i >= nkX) write_lo(raw + 2 * Cfg::A_BYTES / 4, raw + (2 * Cfg::A_BYTES + Cfg::B_BYTES) / 4, Cfg::B_BYTES / 16, ct, TC_CONV_THREADS);
             fence_proxy_async_smem();
             mbar_arrive(&bars.conv[s]);
             if (ct == 0) DBG(8 + 6 * i + 2);
         }
     }
     if (threadIdx.x == 0) DBG(0);
+    if constexpr (BLK) {
+        // ---- blocked Gauss-Seidel sweep on the accumulator ------------------------------------------------------
+        // The accumulator holds D = -(gradient).  Coordinates are processed in blocks of 8: inside a block one thread
+        // per frame updates sequentially (corrections from the block's own deltas in registers); the effect of the
+        // block on all later coordinates, D -= delta[128x8] . G[8 x KP], is one (error-compensated) K = 8 tensor-core
+        // MMA.  No shuffles, no shared-memory traffic proportional to K^2, and D never leaves TMEM.
+        unsigned char* sGr = smem;                                       // G as K-major SWIZZLE_128B chunks [KP/32][KP][128 B]
+        unsigned char* sGl = smem + (size_t)KP * KP * 4;                 // its TF32 residual, same layout
+        float* sDh = reinterpret_cast<float*>(smem + (size_t)2 * KP * KP * 4);   // delta tile 128 x 8, core-matrix interleaved
+        float* sDl = sDh + TC_M * 8;
+        float* sInv = sDl + TC_M * 8;
+        __syncthreads();                                               // idle lanes park here
+        if (lane == 0) mbar_wait(&bars.accum, 0);                      // every MMA has finished reading the stage buffers
+        __syncwarp();
+        tcgen05_fence_after();
+        if (threadIdx.x == 0) DBG(1);
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bars.gload, 2 * KP * KP * 4);
+            for (int c = 0; c < KP / 32; ++c) {
+                tma_load_3d(sGr + (size_t)c * KP * 128, &mapG, &bars.gload, c * 32, 0, b);
+                tma_load_3d(sGl + (size_t)c * KP * 128, &mapGlo, &bars.gload, c * 32, 0, b);
+            }
+        }
+        if (lane == 0) mbar_wait(&bars.gload, 0);
+        __syncwarp();
+        auto g_at = [&](int n, int c) -> float {                       // G[n][c] from the swizzled copy
+            const int cc = c & 31;
+            return *reinterpret_cast<const float*>(sGr + (size_t)(c >> 5) * KP * 128 + n * 128 + ((((cc >> 2) ^ (n & 7))) << 4) + ((cc & 3) << 2));
+        };
+        for (int t = threadIdx.x; t < KP; t += blockDim.x) { const float d = g_at(t, t); sInv[t] = (d != 0.f) ? 1.0f / d : 0.f; }
+        __syncthreads();
+        if (threadIdx.x == 0) DBG(2);
+        float vsum = 0.f;
+        constexpr int NBLK = KP / 8;
+        if (warp >= 4) {
+            const int q = warp & 3, row = q * 32 + lane;
+            const int t = m0 + row;
+            const bool valid = t < T;
+            float* hrow = Ht + (long long)b * h_stride + (long long)t * KP;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+            const int doff = (row >> 3) * 64 + (row & 7) * 4;           // floats: 8-row core matrices of 16 B, K-adjacent cores 128 B apart
+#pragma unroll 1
+            for (int blk = 0; blk < NBLK; ++blk) {
+                float d8[8], a8[8], dl[8];
+                tmem_ld_32x8(taddr + blk * 8, d8);
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (valid) { v0 = *reinterpret_cast<const float4*>(hrow + 8 * blk); v1 = *reinterpret_cast<const float4*>(hrow + 8 * blk + 4); }
+                a8[0] = v0.x; a8[1] = v0.y; a8[2] = v0.z; a8[3] = v0.w; a8[4] = v1.x; a8[5] = v1.y; a8[6] = v1.z; a8[7] = v1.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int tt = 8 * blk + j;
+                    float grad = -d8[j];
+#pragma unroll
+                    for (int i = 0; i < j; ++i) grad = fmaf(g_at(tt, 8 * blk + i), dl[i], grad);
+                    const float inv = sInv[tt];
+                    const float aq = a8[j];
+                    const float pg = (aq == 0.f) ? fminf(0.f, grad) : grad;
+                    const float an = fmaxf(fmaf(-grad, inv, aq), 0.f);
+                    const bool upd = valid && (inv != 0.f);
+                    vsum += valid ? fabsf(pg) : 0.f;
+                    dl[j] = upd ? an - aq : 0.f;
+                    a8[j] = upd ? an : aq;
+                }
+                if (valid) {
+                    *reinterpret_cast<float4*>(hrow + 8 * blk) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+                    *reinterpret_cast<float4*>(hrow + 8 * blk + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+                }
+                if (blk + 1 < NBLK) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split_tf32(dl[j], hi[j], lo[j]);
+                    *reinterpret_cast<float4*>(sDh + doff) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(sDh + doff + 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<float4*>(sDl + doff) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(sDl + doff + 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bars.dready);
+                    if (lane == 0) mbar_wait(&bars.ddone, blk & 1);
+                    __syncwarp();
+                    tcgen05_fence_after();
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idn = make_idesc_tf32(TC_M, KP, 0, 0) | (1u << 13);      // D -= delta . G
+            const uint64_t dAh = make_smem_desc(smem_u32(sDh), 128, 256, 0);          // K-major, no swizzle
+            const uint64_t dAl = make_smem_desc(smem_u32(sDl), 128, 256, 0);
+#pragma unroll 1
+            for (int blk = 0; blk + 1 < NBLK; ++blk) {
+                if (lane == 0) {
+                    mbar_wait(&bars.dready, blk & 1);
+                    tcgen05_fence_after();
+                    const uint32_t boff = (uint32_t)(blk >> 2) * KP * 128 + (uint32_t)(blk & 3) * 32;
+                    const uint64_t dBr = make_smem_desc(smem_u32(sGr) + boff, 16, 1024);
+                    const uint64_t dBl = make_smem_desc(smem_u32(sGl) + boff, 16, 1024);
+                    mma_tf32_ss(tmem, dAh, dBr, idn, 1);
+                    mma_tf32_ss(tmem, dAh, dBl, idn, 1);
+                    mma_tf32_ss(tmem, dAl, dBr, idn, 1);
+                    mma_commit(&bars.ddone);
+                }
+                __syncwarp();
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, KP);
+        const float tot = block_sum(vsum, s_red);
+        if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+        if (threadIdx.x == 0) DBG(3);
+        return;
+    }
     // ---- epilogue: accumulator -> shared, Gram -> shared, sweep --------------------------------------------
     float* sC = reinterpret_cast<float*>(smem);                    // [128][CPITCH] (aliases the pipeline buffers)
     float* sG = sC + TC_M * CPITCH;                                // [KP][GPITCH]
@@ -417,6 +533,15 @@ wt_split_kernel(const float* __restrict__ W, long long w_stride, int F, int KP, 
     }
 }
 
+// Glo = G - trunc_tf32(G) for the KP x KP Gram matrices; grid = (ceil(KP*KP/256), B)
+__global__ void __launch_bounds__(kThreads)
+g_split_kernel(const float* __restrict__ G, float* __restrict__ Glo, int n, const ClipState* __restrict__ st) {
+    const int b = blockIdx.y;
+    if (st[b].done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float h, l; split_tf32(G[(long long)b * n + i], h, l); Glo[(long long)b * n + i] = l; }
+}
+
 // out[b][e] = sum_s partial[b][s][e]  (fixed order); grid = (ceil(n4/256), B)
 __global__ void __launch_bounds__(kThreads)
 reduce_splits_kernel(const float* __restrict__ partial, int S, long long n4, float* __restrict__ out, long long out_stride,
@@ -463,7 +588,12 @@ static cudaError_t tc_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
                  wk.tc_Wt, wk.tc_WtLo, (long long)KP * ldw, p.state);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(h_step_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
+    AINMF_LAUNCH(g_split_kernel, dim3(ceil_div(KP * KP, kThreads), p.B), dim3(kThreads), 0, s, wk.WtW, wk.tc_GLo, KP * KP, p.state);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    static int blk_mode = -1;
+    if (blk_mode < 0) { const char* m_ = getenv("AINMF_TC_SWEEP"); blk_mode = (m_ && m_[0] == 's') ? 0 : 1; }   // "shfl" selects the shuffle sweep
+    auto kern = blk_mode ? h_step_tc_kernel<KP, true> : h_step_tc_kernel<KP, false>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
     static long long* dbg = nullptr;
     static int dbg_left = -1;
     if (dbg_left < 0) {
@@ -471,8 +601,8 @@ static cudaError_t tc_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
         dbg_left = (e_ && e_[0] == '1') ? 3 : 0;
         if (dbg_left) { cudaMalloc((void**)&dbg, 4096 * sizeof(long long)); cudaMemset(dbg, 0, 4096 * sizeof(long long)); }
     }
-    AINMF_LAUNCH(h_step_tc_kernel<KP>, dim3(ceil_div(p.T, TC_M), p.B), dim3(kThreads), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX),
-                 as_map(wk.tc->mapWt), as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), p.F, p.T, wk.WtW,
+    AINMF_LAUNCH(kern, dim3(ceil_div(p.T, TC_M), p.B), dim3(kThreads), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX),
+                 as_map(wk.tc->mapWt), as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), as_map(wk.tc->mapGlo), p.F, p.T, wk.WtW,
                  p.Ht, p.h_stride, wk.violH, p.state,
                  dbg_left > 0 ? dbg : nullptr);
     if (dbg_left > 0) {
@@ -502,6 +632,7 @@ int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* m) {
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapHmn), p.Ht, KP, T, B, KP, (uint64_t)p.h_stride, 32, TC_BK, 1);
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapHk), p.Ht, KP, T, B, KP, (uint64_t)p.h_stride, TC_BK, TC_M, 0);
     if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapG), wk->WtW, KP, KP, B, KP, KP * KP, TC_BK, (uint32_t)KP, 0);
+    if (!rc) rc = make_tensor_map_3d(as_map_ptr(&m->mapGlo), wk->tc_GLo, KP, KP, B, KP, KP * KP, TC_BK, (uint32_t)KP, 0);
     wk->tc = m;
     return rc;
 }

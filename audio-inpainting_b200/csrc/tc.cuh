@@ -91,6 +91,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- descriptors --------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B.  Addresses/offsets in bytes (16-byte granular).
 //   K-major operand  (rows = M or N index, 128 B = 32 tf32 of K per row): SBO = byte stride between 8-row groups
