@@ -139,6 +139,8 @@ struct NmfWork {
     int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
     float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed, and its TF32 residual
     float* tc_GLo = nullptr;                      // [B][KP][KP]: TF32 residual of W^T W
+    float* tc_blobs = nullptr;                    // [B][KP/8][16*KP]: per-block update operands of the sweep (nmf_ts.cu: g_prep_kernel)
+    float* tc_scal = nullptr;                     // [B][KP/8][136]: per-block sweep scalars
     const TcMaps* tc = nullptr;
     float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
     float *violW = nullptr, *violH = nullptr;
@@ -160,6 +162,7 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk);
 int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* maps);
 cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // X.Ht partials + HHt
 cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // Wt split, X^T.W + H sweep
+cudaError_t nmf_ts_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // persistent TMEM-operand H step (nmf_ts.cu)
 void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
 // multiplicative update, Frobenius loss (sklearn solver='mu': $SP/sklearn/decomposition/_nmf.py:536-549,615-624,

@@ -903,7 +903,7 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
     n += al256(sizeof(float) * (size_t)B * gp * KP * KP);                          // gram partials
     n += al256(sizeof(unsigned) * (size_t)B);                                      // counters
     n += al256(sizeof(float) * (size_t)B * (xs + 1) * F * KP);                      // xht partials
-    if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)) + al256(sizeof(float) * (size_t)B * KP * KP); // Wt, Wt_lo, G_lo
+    if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)) + al256(sizeof(float) * (size_t)B * KP * KP) + al256(sizeof(float) * (size_t)B * (KP / 8) * (16 * KP)) + al256(sizeof(float) * (size_t)B * (KP / 8) * 136); // Wt, Wt_lo, G_lo, sweep blobs + scalars
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
     if (wk.want_mu) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
@@ -924,6 +924,8 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
         wk->tc_Wt = (float*)take(sizeof(float) * (size_t)B * KP * round_up(F, 4));
         wk->tc_WtLo = (float*)take(sizeof(float) * (size_t)B * KP * round_up(F, 4));
         wk->tc_GLo = (float*)take(sizeof(float) * (size_t)B * KP * KP);
+        wk->tc_blobs = (float*)take(sizeof(float) * (size_t)B * (KP / 8) * (16 * KP));
+        wk->tc_scal = (float*)take(sizeof(float) * (size_t)B * (KP / 8) * 136);
     }
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);

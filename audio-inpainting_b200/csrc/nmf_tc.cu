@@ -588,6 +588,9 @@ static cudaError_t tc_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
                  wk.tc_Wt, wk.tc_WtLo, (long long)KP * ldw, p.state);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    static int ts_mode = -1;       // AINMF_TC_MODE=ss selects the shared-memory-operand kernel below; default: nmf_ts.cu
+    if (ts_mode < 0) { const char* m_ = getenv("AINMF_TC_MODE"); ts_mode = (m_ && m_[0] == 's') ? 0 : 1; }
+    if (ts_mode) return nmf_ts_hstep(p, wk, s);
     AINMF_LAUNCH(g_split_kernel, dim3(ceil_div(KP * KP, kThreads), p.B), dim3(kThreads), 0, s, wk.WtW, wk.tc_GLo, KP * KP, p.state);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     static int blk_mode = -1;

@@ -13,11 +13,13 @@ constexpr int PM = 128;       // M
 constexpr int PBK = 32;       // contraction elements per stage (one 128-byte swizzle row)
 
 // mode 0: A [128][Kd], B [N][Kd]  (K-major both);  mode 1: At [Kd][128], Bt [Kd][N] (MN-major both)
-// split: 0 = single pass on the raw fp32 bits; 1 = hi/lo split in shared memory + 3 passes
+// mode 2: as mode 0, but the A operand is placed in TMEM by the threads (tcgen05.st: lane = row, one column per
+//         contraction element; raw bits as a_hi, a_lo beside it) and the MMA takes A from TMEM, B from shared memory
+// split: 0 = single pass on the raw fp32 bits; 1 = hi/lo split + 3 passes
 template <int N>
 __global__ void __launch_bounds__(128)
 tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Kd, int mode,
-                int split, float* __restrict__ D) {
+                int split, float* __restrict__ D, const float* __restrict__ Ag) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_full, bar_mma;
     __shared__ uint32_t tmem_slot;
@@ -33,7 +35,8 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_init(&bar_mma, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, N < 32 ? 32 : N);
+    const uint32_t ncols = (mode == 2) ? 512 : (N < 32 ? 32 : N);
+    if (warp == 1) tmem_alloc(&tmem_slot, ncols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -41,7 +44,7 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bar_full, (uint32_t)stages * (a_bytes + b_bytes));
         for (int s = 0; s < stages; ++s) {
-            if (mode == 0) {
+            if (mode == 0 || mode == 2) {
                 tma_load_3d(sA + (size_t)s * PM * PBK, &mapA, &bar_full, s * PBK, 0, 0);
                 tma_load_3d(sB + (size_t)s * N * PBK, &mapB, &bar_full, s * PBK, 0, 0);
             } else {
@@ -59,10 +62,23 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = threadIdx.x; i < nb; i += blockDim.x) { float h, l; split_tf32(sB[i], h, l); sB[i] = h; sBlo[i] = l; }
         fence_proxy_async_smem();
     }
+    if (mode == 2) {   // thread = row of A: raw values -> TMEM columns [N, N+Kd), residuals -> [N+Kd, N+2Kd)
+        const int row = threadIdx.x;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + N;
+        for (int c0 = 0; c0 < Kd; c0 += 8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float v = Ag[(size_t)row * Kd + c0 + j]; float h; split_tf32(v, h, lo[j]); hi[j] = v; }
+            tmem_st_32x8(tbase + c0, hi);
+            tmem_st_32x8(tbase + Kd + c0, lo);
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc_tf32(PM, N, mode, mode);
+        const uint32_t idesc = make_idesc_tf32(PM, N, mode == 1, mode == 1);
         uint32_t acc = 0;
         for (int s = 0; s < stages; ++s) {
             for (int k8 = 0; k8 < PBK / 8; ++k8) {
@@ -71,6 +87,12 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const float* a = (pss == 2 ? sAlo : sA) + (size_t)s * PM * PBK;
                     const float* b = (pss == 1 ? sBlo : sB) + (size_t)s * N * PBK;
                     uint64_t da, db;
+                    if (mode == 2) {
+                        db = make_smem_desc(smem_u32(b) + k8 * 32, 16, 1024);
+                        mma_tf32_ts(tmem, tmem + N + (pss == 2 ? Kd : 0) + s * PBK + k8 * 8, db, idesc, acc);
+                        acc = 1;
+                        continue;
+                    }
                     if (mode == 0) {
                         da = make_smem_desc(smem_u32(a) + k8 * 32, 16, 1024);
                         db = make_smem_desc(smem_u32(b) + k8 * 32, 16, 1024);
@@ -97,7 +119,7 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, N < 32 ? 32 : N);
+    if (warp == 1) tmem_dealloc(tmem, ncols);
 }
 
 }  // namespace ainmf
@@ -107,7 +129,7 @@ extern "C" int ainmf_tc_probe(int mode, int split, int N, int Kd, const float* A
     if ((N != 64 && N != 128) || Kd % PBK != 0 || Kd <= 0 || Kd > 128) return -1;
     CUtensorMap ma, mb;
     int rc;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
         rc = make_tensor_map_3d(&ma, A, Kd, PM, 1, Kd, (uint64_t)Kd * PM, PBK, PM);
         if (!rc) rc = make_tensor_map_3d(&mb, B, Kd, N, 1, Kd, (uint64_t)Kd * N, PBK, N);
     } else {
@@ -121,10 +143,10 @@ extern "C" int ainmf_tc_probe(int mode, int split, int N, int Kd, const float* A
     cudaError_t e;
     if (N == 64) {
         e = cudaFuncSetAttribute(tc_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_probe_kernel<64><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D);
+        if (e == cudaSuccess) tc_probe_kernel<64><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A);
     } else {
         e = cudaFuncSetAttribute(tc_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_probe_kernel<128><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D);
+        if (e == cudaSuccess) tc_probe_kernel<128><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A);
     }
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();

@@ -28,7 +28,7 @@ def run_probe(mode, split, N, Kd, A, B):
     return D.cpu().numpy()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("N", [64, 128])
 def test_probe_single_pass_and_split(mode, N):
     if not torch.cuda.is_available():
@@ -37,8 +37,8 @@ def test_probe_single_pass_and_split(mode, N):
     Kd = 96
     A = rng.standard_normal((128, Kd)).astype(np.float32)       # logical A [M][K], B [N][K]
     B = rng.standard_normal((N, Kd)).astype(np.float32)
-    Ain = A if mode == 0 else np.ascontiguousarray(A.T)
-    Bin = B if mode == 0 else np.ascontiguousarray(B.T)
+    Ain = A if mode != 1 else np.ascontiguousarray(A.T)
+    Bin = B if mode != 1 else np.ascontiguousarray(B.T)
     ref64 = A.astype(np.float64) @ B.astype(np.float64).T
     ref_tr = trunc_tf32(A).astype(np.float64) @ trunc_tf32(B).astype(np.float64).T
     scale = np.abs(ref64).max()
