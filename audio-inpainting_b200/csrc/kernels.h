@@ -131,7 +131,7 @@ struct NmfProblem {
 };
 // TMA tensor maps of the tensor-core path (each an opaque 128-byte CUtensorMap; built on the host per problem)
 struct alignas(64) TcMapBlob { unsigned char b[128]; };
-struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXmn, mapHmn, mapHk, mapG, mapGlo; };
+struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXs, mapHs, mapHmn, mapHk, mapG, mapGlo; };
 
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;
@@ -163,6 +163,7 @@ int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* maps);
 cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // X.Ht partials + HHt
 cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // Wt split, X^T.W + H sweep
 cudaError_t nmf_ts_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // persistent TMEM-operand H step (nmf_ts.cu)
+cudaError_t nmf_ts_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);   // persistent TMEM-operand X.Ht + Gram (nmf_ts.cu)
 void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk);
 cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
 // multiplicative update, Frobenius loss (sklearn solver='mu': $SP/sklearn/decomposition/_nmf.py:536-549,615-624,

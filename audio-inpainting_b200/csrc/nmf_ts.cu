@@ -1,9 +1,16 @@
 // nmf_ts.cu -- H half-step of the CD-NMF iteration as ONE persistent, warp-specialised sm_100a kernel in which the
 // spectrogram operand never goes back to shared memory:
 //
-//   TMA (X chunk, W^T chunk hi/lo) -> shared -> converter warps read their frame's row once, split it into
-//   tf32 hi/lo in registers and store both with tcgen05.st into TMEM -> tcgen05.mma with the A operand taken FROM
-//   TMEM (B = W^T chunk from shared) accumulates  D = X_tile.W - Ht_tile.(W^T W) = -(gradient)  in TMEM.
+//   TMA (X chunk, W^T chunk: tf32 tile + bf16 cross tile) -> shared -> converter warps read their frame's row once,
+//   build the two A operands in registers and store them with tcgen05.st into TMEM -> tcgen05.mma with the A operand
+//   taken FROM TMEM (B = W^T chunk from shared) accumulates  D = X_tile.W - Ht_tile.(W^T W) = -(gradient)  in TMEM.
+//
+// Error compensation (a single TF32 pass breaks the reference's tolerances): with v_hi = v truncated to
+// tf32 and v_lo = v - v_hi,   a*b ~= a_hi*b_hi  +  (a_lo*b_hi + a_hi*b_lo).   A tcgen05.mma costs ~128 cycles whatever
+// its N <= 256 (measured, tests/mma_bench.py), so the instruction count is what matters: the main term is one
+// kind::tf32 instruction per 8 contraction elements, and BOTH cross terms are one kind::f16 (bf16, K = 16)
+// instruction whose K dimension is the concatenation [a_lo | a_hi].[b_hi ; b_lo]; the cross terms are 2^-11 of the
+// result, so bf16 factors keep the sum accurate to ~2^-20 (tests/test_gpu_tc.py).
 //
 // Compared with the shared-memory-operand kernel (nmf_tc.cu) this removes the lo-tile write and the three operand
 // reads of the X tile from shared memory (136 KB -> 72 KB of shared-memory traffic per 16 KB of X at K = 64), which
@@ -91,7 +98,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGlo, int F, int T, int B,
                  const float* __restrict__ blobs /*[B][NBLK][16 KP]*/, const float* __restrict__ scal /*[B][NBLK][TS_SC]*/,
                  float* __restrict__ Ht, long long h_stride,
-                 float* __restrict__ viol /*[B][nH]*/, const ClipState* __restrict__ st, long long* __restrict__ dbg) {
+                 float* __restrict__ viol /*[B][nH]*/, const ClipState* __restrict__ st, long long* __restrict__ dbg, int exp_flags) {
     using Cfg = TsCfg<KP>;
     constexpr int NSS = Cfg::NSS, NAS = Cfg::NAS, NBLK = Cfg::NBLK, NG = Cfg::NG;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -138,6 +145,14 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     const uint32_t s = it % NSS, ph = (it / NSS) & 1;
                     mbar_wait(&bars.empty[s], ph ^ 1);
                     unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
+                    if (exp_flags && i < nkX) {       // timing experiments only (wrong results): 1 = no Wlo, 2 = no W, 4 = no X
+                        const uint32_t bytes = ((exp_flags & 4) ? 0 : Cfg::X_BYTES) + ((exp_flags & 2) ? 0 : Cfg::B_BYTES) + ((exp_flags & 3) ? 0 : Cfg::B_BYTES);
+                        if (bytes) mbar_arrive_expect_tx(&bars.full[s], bytes); else mbar_arrive(&bars.full[s]);
+                        if (!(exp_flags & 4)) tma_load_3d(stg, &mapX, &bars.full[s], i * TS_BK, m0, b);
+                        if (!(exp_flags & 2)) tma_load_3d(stg + Cfg::X_BYTES, &mapWt, &bars.full[s], i * TS_BK, 0, b);
+                        if (!(exp_flags & 3)) tma_load_3d(stg + Cfg::X_BYTES + Cfg::B_BYTES, &mapWtLo, &bars.full[s], i * TS_BK, 0, b);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bars.full[s], Cfg::X_BYTES + 2 * Cfg::B_BYTES);
                     if (i < nkX) {
                         tma_load_3d(stg, &mapX, &bars.full[s], i * TS_BK, m0, b);
@@ -154,8 +169,8 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     } else if (warp == 1) {
         // ---------------- MMA issuer: D[buf] = X_tile.W - Ht_tile.G ----------------
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 0);
-            const uint32_t idesc_neg = idesc | (1u << 13);           // negate A
+            const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 0), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
+            const uint32_t neg = 1u << 13;                            // negate A
             uint32_t it = 0, tl = 0;
             while (tiles.next(b, mt)) {
                 const uint32_t buf = tl & 1;
@@ -169,16 +184,15 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
                     mbar_wait(&bars.conv[a], (it / NAS) & 1);
                     tcgen05_fence_after();
-                    const uint32_t id = (i < nkX) ? idesc : idesc_neg;
+                    const uint32_t ng = (i < nkX) ? 0u : neg;
                     const uint64_t d_bh = make_smem_desc(smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::X_BYTES), 16, 1024);
                     const uint64_t d_bl = d_bh + (uint64_t)(Cfg::B_BYTES >> 4);
                     const uint32_t acol = tmem + Cfg::COL_A + a * 64;
 #pragma unroll
                     for (int k8 = 0; k8 < TS_BK / 8; ++k8) {
                         const uint64_t o = (uint64_t)(k8 * 32 >> 4);
-                        mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, id, (i > 0 || k8 > 0) ? 1u : 0u);
-                        mma_tf32_ts(dcol, acol + k8 * 8, d_bl + o, id, 1);
-                        mma_tf32_ts(dcol, acol + 32 + k8 * 8, d_bh + o, id, 1);
+                        mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, idesc | ng, (i > 0 || k8 > 0) ? 1u : 0u);
+                        mma_bf16_ts(dcol, acol + 32 + k8 * 8, d_bl + o, idesc16 | ng, 1);
                     }
                     mma_commit(&bars.empty[s]);
                     mma_commit(&bars.aempty[a]);
@@ -193,7 +207,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         // Block blk of a tile needs an update MMA only if blk <= NBLK-3: the sweep threads themselves carry a block's
         // deltas into the NEXT block's 8 coordinates (look-ahead), so an update has one whole block of slack.
         if (lane == 0) {
-            const uint32_t idn = make_idesc_tf32(TS_M, KP, 0, 0) | (1u << 13);
+            const uint32_t idn = make_idesc_tf32(TS_M, KP, 0, 0) | (1u << 13), idn16 = make_idesc_bf16(TS_M, KP, 0, 0) | (1u << 13);
             TsTiles cur{(int)blockIdx.x, (int)gridDim.x, B * nH, nH, st};     // operand load cursor
             int cb = 0, cmt = 0, cblk = 0;
             bool cmore = cur.next(cb, cmt);
@@ -236,8 +250,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     const uint64_t d_gh = make_smem_desc(bh, KP * 16, 128, 0);
                     const uint64_t d_gl = make_smem_desc(bh + 8 * KP * 4, KP * 16, 128, 0);
                     mma_tf32_ts(dcol, tmem + Cfg::COL_DELTA, d_gh, idn, 1);
-                    mma_tf32_ts(dcol, tmem + Cfg::COL_DELTA, d_gl, idn, 1);
-                    mma_tf32_ts(dcol, tmem + Cfg::COL_DELTA + 8, d_gh, idn, 1);
+                    mma_bf16_ts(dcol, tmem + Cfg::COL_DELTA + 8, d_gl, idn16, 1);
                     mma_commit(&bars.ddone);
                     mma_commit(&bars.gempty[slot]);
                 }
@@ -263,14 +276,14 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 tcgen05_fence_after();
                 if (kd) { const long long c = clock64(); k_ae += c - k_t; k_t = c; }
                 const unsigned char* xr = smem + (size_t)s * Cfg::STAGE_BYTES + row * 128;
-                float hi[32], lo[32];
+                float hi[32], lo[32];                                 // lo: the bf16 cross operand, [lo(8) | hi(8)] per 8 elements
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 v = *reinterpret_cast<const float4*>(xr + ((j ^ sw) << 4));
                     hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { float h; split_tf32(hi[j], h, lo[j]); }
+                for (int j = 0; j < 4; ++j) cross_pack8(hi + 8 * j, lo + 8 * j, true);
                 if (kd) { const long long c = clock64(); k_rd += c - k_t; k_t = c; }
                 tmem_st_32x32(tlane + a * 64, hi);                    // raw bits: the tensor core ignores the low 13
                 tmem_st_32x32(tlane + a * 64 + 32, lo);
@@ -402,7 +415,8 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     } else {                                          // ... and this block's deltas go to the tensor core
                         float hl[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { float h; split_tf32(dl[j], h, hl[8 + j]); hl[j] = dl[j]; }
+                        for (int j = 0; j < 8; ++j) hl[j] = dl[j];
+                        cross_pack8(dl, hl + 8, true);
                         TS_TIC();
                         tmem_st_32x16(tlane + Cfg::COL_DELTA, hl);
                         tmem_wait_st();
@@ -441,12 +455,226 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================
+// W half-step, local part:  [X | Ht]^T Ht  -> X.Ht partials (F x KP) and the Gram Ht^T Ht (KP x KP), split over time.
+// Persistent, same scheme as the H step: work items (clip, time split, 128-column tile of the virtual matrix
+// [ X (ceil(F/32) slabs of 32 columns) | Ht (KP/32 slabs) ]), round-robin over the CTAs.  Per chunk of 32 frames:
+//   TMA: 4 column slabs [32 t][32 cols] of the tile (dense), the Ht chunk as the MN-major tf32 B operand
+//        (SWIZZLE_128B_ATOM_32B) and once more as dense slabs for the threads;
+//   converters: thread = column of the tile = TMEM lane: 32 frames of its column -> tf32 A operand + bf16 cross operand
+//        (tcgen05.st); thread n < KP also turns column n of the dense Ht chunk into row n of the K-major bf16 cross
+//        operand of B in shared memory ([hi(8) | lo(8)] per 8 frames);
+//   MMA:  per 8 frames one kind::tf32 (A from TMEM, B = raw Ht chunk) and one kind::f16 instruction (cross terms);
+//   epilogue warps store finished accumulators (double-buffered) to the partial buffers.
+// =====================================================================================================
+template <int KP> struct XtCfg {
+    static constexpr int NSS = (KP == 64) ? 5 : 3;               // shared-memory stages
+    static constexpr int NAS = (KP == 64) ? 5 : 3;               // TMEM A stages
+    static constexpr int SLAB = 32 * TS_BK * 4;                  // 4 KB: 32 frames x 32 columns
+    static constexpr int A_BYTES = 4 * SLAB;                     // 16 KB
+    static constexpr int B_BYTES = KP * TS_BK * 4;               // 8 / 16 KB
+    static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;    // A slabs | B raw (MN-major) | B dense | B cross (K-major bf16)
+    static constexpr int SMEM_BYTES = NSS * STAGE_BYTES + 1024;
+    static constexpr int COL_D = 0, COL_A = 2 * KP;
+    static_assert(COL_A + NAS * 64 <= 512, "TMEM budget");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+struct XtItems {
+    int item, step, n, mtiles, S;
+    const ClipState* st;
+    __device__ __forceinline__ bool next(int& b, int& split, int& mt) {
+        while (item < n) {
+            mt = item % mtiles;
+            const int r = item / mtiles;
+            split = r % S;
+            b = r / S;
+            item += step;
+            if (!st[b].done) return true;
+        }
+        return false;
+    }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__ CUtensorMap mapHs,
+              const __grid_constant__ CUtensorMap mapHmn, int F, int T, int B, int S, int mtiles, int frames_per_split,
+              float* __restrict__ xht_partial /*[B][S][F][KP]*/, float* __restrict__ gram_partial /*[B][S][KP][KP]*/,
+              const ClipState* __restrict__ st) {
+    using Cfg = XtCfg<KP>;
+    constexpr int NSS = Cfg::NSS, NAS = Cfg::NAS, NB = KP / 32;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) TsBarriers bars;
+    __shared__ uint32_t tmem_slot;
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nxs = (F + 31) / 32;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSS; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int a = 0; a < NAS; ++a) { mbar_init(&bars.conv[a], 4); mbar_init(&bars.aempty[a], 1); }
+        for (int j = 0; j < 2; ++j) { mbar_init(&bars.dfull[j], 1); mbar_init(&bars.dempty[j], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&mapXs); tma_prefetch_desc(&mapHs); tma_prefetch_desc(&mapHmn);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    XtItems items{(int)blockIdx.x, (int)gridDim.x, B * S * mtiles, mtiles, S, st};
+    int b, split, mt;
+    auto chunks_of = [&](int sp) {
+        const int t_begin = sp * frames_per_split;
+        const int t_end = min(T, t_begin + frames_per_split);
+        return (t_end - t_begin + TS_BK - 1) / TS_BK;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            while (items.next(b, split, mt)) {
+                const int nk = chunks_of(split), t_begin = split * frames_per_split;
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const uint32_t s = it % NSS;
+                    mbar_wait(&bars.empty[s], ((it / NSS) & 1) ^ 1);
+                    unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
+                    const int t0 = t_begin + i * TS_BK;           // frames past T load zeros; split boundaries are multiples of 32
+                    mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int v = 4 * mt + j;
+                        if (v < nxs) tma_load_3d(stg + j * Cfg::SLAB, &mapXs, &bars.full[s], 32 * v, t0, b);
+                        else tma_load_3d(stg + j * Cfg::SLAB, &mapHs, &bars.full[s], 32 * (v - nxs), t0, b);   // >= KP: zero fill
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        tma_load_3d(stg + Cfg::A_BYTES + j * Cfg::SLAB, &mapHmn, &bars.full[s], 32 * j, t0, b);
+                        tma_load_3d(stg + Cfg::A_BYTES + Cfg::B_BYTES + j * Cfg::SLAB, &mapHs, &bars.full[s], 32 * j, t0, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 1), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
+            uint32_t it = 0, tl = 0;
+            while (items.next(b, split, mt)) {
+                const int nk = chunks_of(split);
+                const uint32_t buf = tl & 1;
+                mbar_wait(&bars.dempty[buf], ((tl >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t dcol = tmem + Cfg::COL_D + buf * KP;
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const uint32_t s = it % NSS, a = it % NAS;
+                    mbar_wait(&bars.full[s], (it / NSS) & 1);
+                    mbar_wait(&bars.conv[a], (it / NAS) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t b_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+                    const uint64_t d_bx = make_smem_desc(b_raw + 2 * Cfg::B_BYTES, 16, 1024);
+                    const uint32_t acol = tmem + Cfg::COL_A + a * 64;
+#pragma unroll
+                    for (int k8 = 0; k8 < TS_BK / 8; ++k8) {
+                        const uint64_t d_br = make_smem_desc(b_raw + k8 * 1024, Cfg::SLAB, 512, kLayoutSw128Base32);
+                        mma_tf32_ts(dcol, acol + k8 * 8, d_br, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
+                        mma_bf16_ts(dcol, acol + 32 + k8 * 8, d_bx + (uint64_t)(k8 * 32 >> 4), idesc16, 1);
+                    }
+                    mma_commit(&bars.empty[s]);
+                    mma_commit(&bars.aempty[a]);
+                }
+                mma_commit(&bars.dfull[buf]);
+                ++tl;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        const int q = warp & 3, col = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_A;
+        uint32_t it = 0;
+        while (items.next(b, split, mt)) {
+            const int nk = chunks_of(split);
+            for (int i = 0; i < nk; ++i, ++it) {
+                const uint32_t s = it % NSS, a = it % NAS;
+                if (lane == 0) {
+                    mbar_wait(&bars.full[s], (it / NSS) & 1);
+                    mbar_wait(&bars.aempty[a], ((it / NAS) & 1) ^ 1);
+                }
+                __syncwarp();
+                tcgen05_fence_after();
+                unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
+                {   // A: column `col` of the tile over the chunk's 32 frames
+                    const float* xs = reinterpret_cast<const float*>(stg + q * Cfg::SLAB) + lane;
+                    float hi[32], cx[32];
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) hi[t] = xs[t * 32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cross_pack8(hi + 8 * j, cx + 8 * j, true);
+                    tmem_st_32x32(tlane + a * 64, hi);
+                    tmem_st_32x32(tlane + a * 64 + 32, cx);
+                }
+                if (col < KP) {   // B cross operand: row n = col, 4 groups of 8 frames -> 8 chunks of 16 bytes (128-byte swizzle)
+                    const float* hs = reinterpret_cast<const float*>(stg + Cfg::A_BYTES + Cfg::B_BYTES + (col >> 5) * Cfg::SLAB) + (col & 31);
+                    unsigned char* br = stg + Cfg::A_BYTES + 2 * Cfg::B_BYTES + col * 128;
+                    float v[32], w[8];
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) v[t] = hs[t * 32];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        cross_pack8(v + 8 * g, w, false);
+                        *reinterpret_cast<float4*>(br + (((2 * g) ^ (col & 7)) << 4)) = make_float4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<float4*>(br + (((2 * g + 1) ^ (col & 7)) << 4)) = make_float4(w[4], w[5], w[6], w[7]);
+                    }
+                    fence_proxy_async_smem();
+                }
+                tmem_wait_st();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.conv[a]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ---------------- epilogue: rows of the accumulator straight to the partial buffers ----------------
+        const int q = warp & 3;
+        uint32_t tl = 0;
+        while (items.next(b, split, mt)) {
+            const uint32_t buf = tl & 1;
+            if (lane == 0) mbar_wait(&bars.dfull[buf], (tl >> 1) & 1);
+            __syncwarp();
+            tcgen05_fence_after();
+            const int vcol = 128 * mt + q * 32 + lane;             // virtual column = output row
+            float* dst = nullptr;
+            if (vcol < 32 * nxs) {
+                if (vcol < F) dst = xht_partial + ((((long long)b * S + split) * F) + vcol) * KP;
+            } else if (vcol - 32 * nxs < KP) {
+                dst = gram_partial + ((((long long)b * S + split) * KP) + (vcol - 32 * nxs)) * KP;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < KP; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_D + buf * KP + c0, v);
+                if (dst) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.dempty[buf]);
+            ++tl;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+
 // Per clip and per block of 8 coordinates:
 //   blobs: the rows G[8blk .. 8blk+8)[0..KP) of the Gram matrix laid out as the K-major (no swizzle) [N = KP][K = 8]
-//          operand of the sweep update -- raw values, then their TF32 residuals;
+//          operand of the sweep update -- raw values (tf32 main term), then the bf16 cross operand;
 //   scal : what the sweep threads read themselves: the diagonal block G[8blk+j][8blk+i], the look-ahead block
 //          G[8blk+i][8(blk+1)+c] and the reciprocals of the block's diagonal (0 where the diagonal is 0);
-//   Glo = G - trunc_tf32(G) for the contraction's Ht.G chunks.
+//   Glo (GX): the bf16 cross operand of G's rows for the contraction's Ht.G chunks (same footprint as G).
 // grid = (KP/8, B)
 __global__ void __launch_bounds__(kThreads)
 g_prep_kernel(const float* __restrict__ G, float* __restrict__ Glo, float* __restrict__ blobs, float* __restrict__ scal, int KP,
@@ -459,12 +687,20 @@ g_prep_kernel(const float* __restrict__ G, float* __restrict__ Glo, float* __res
     for (int idx = threadIdx.x; idx < 8 * KP; idx += blockDim.x) {
         const int j = idx / KP, n = idx - j * KP;
         const float v = Gb[(8 * blk + j) * KP + n];
-        float h, l;
-        split_tf32(v, h, l);
-        const int o = ((j >> 2) * KP + n) * 4 + (j & 3);
-        blob[o] = v;
-        blob[8 * KP + o] = l;
-        Glo[(long long)b * KP * KP + (8 * blk + j) * KP + n] = l;
+        blob[((j >> 2) * KP + n) * 4 + (j & 3)] = v;
+    }
+    // cross operands (tc::cross_pack8, B-side order [hi(8) | lo(8)]): rows n of the [N = KP][K = 16 bf16] update operand
+    // (two 8-element cores, KP*16 bytes apart) and the same 8 words as columns 8blk..8blk+7 of row n of GX
+    for (int n = threadIdx.x; n < KP; n += blockDim.x) {
+        float v[8], w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = Gb[(8 * blk + j) * KP + n];          // G[8blk+j][n] = G[n][8blk+j]
+        cross_pack8(v, w, false);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            blob[8 * KP + ((j >> 2) * KP + n) * 4 + (j & 3)] = w[j];
+            Glo[(long long)b * KP * KP + n * KP + 8 * blk + j] = w[j];
+        }
     }
     if (threadIdx.x < 64) {
         const int j = threadIdx.x >> 3, i = threadIdx.x & 7;
@@ -496,6 +732,8 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     }
     AINMF_LAUNCH(g_prep_kernel, dim3(KP / 8, p.B), dim3(kThreads), 0, s, wk.WtW, wk.tc_GLo, wk.tc_blobs, wk.tc_scal, KP, p.state);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    static int exp_flags = -1;
+    if (exp_flags < 0) { const char* x_ = getenv("AINMF_TS_EXP"); exp_flags = x_ ? atoi(x_) : 0; }
     static long long* dbg = nullptr;
     static int dbg_left = -1;
     if (dbg_left < 0) {
@@ -509,7 +747,7 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     AINMF_LAUNCH(h_step_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX), as_map(wk.tc->mapWt),
                  as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), as_map(wk.tc->mapGlo), p.F, p.T, p.B,
-                 wk.tc_blobs, wk.tc_scal, p.Ht, p.h_stride, wk.violH, p.state, dbg_left > 0 ? dbg : nullptr);
+                 wk.tc_blobs, wk.tc_scal, p.Ht, p.h_stride, wk.violH, p.state, dbg_left > 0 ? dbg : nullptr, exp_flags);
     if (dbg_left > 0) {
         --dbg_left;
         long long hbuf[8 * 84];
@@ -530,6 +768,27 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
 
 cudaError_t nmf_ts_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
     return p.KP == 64 ? ts_hstep_impl<64>(p, wk, s) : ts_hstep_impl<128>(p, wk, s);
+}
+
+template <int KP>
+static cudaError_t ts_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    using Cfg = XtCfg<KP>;
+    static int n_sm = 0;
+    cudaError_t e;
+    if (!n_sm) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(xht_ts_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
+    }
+    const long long items = (long long)p.B * wk.tc_splits * wk.tc_mtiles;
+    const int grid = (int)(items < n_sm ? items : n_sm);
+    AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
+                 as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state);
+    return cudaGetLastError();
+}
+cudaError_t nmf_ts_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
+    return p.KP == 64 ? ts_half1_impl<64>(p, wk, s) : ts_half1_impl<128>(p, wk, s);
 }
 
 }  // namespace ainmf

@@ -170,6 +170,39 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulate; A from TMEM: each 32-bit column holds two
+// consecutive K elements (even element in the low half).
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format: F32
+    d |= 1u << 7;                    // A format: BF16
+    d |= 1u << 10;                   // B format: BF16
+    d |= (uint32_t)(a_mn & 1) << 15;
+    d |= (uint32_t)(b_mn & 1) << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// two floats -> packed bf16x2 (round to nearest even): lo in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -181,6 +214,21 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;                     // exact; |lo| < 2^-10 |v|; the tensor core keeps its top 10 mantissa bits
 }
 
+// Cross-term operand of 8 consecutive contraction elements: 8 words = 16 bf16.  `first_lo` selects the A-side order
+// [lo(8) | hi(8)]; the B side is [hi(8) | lo(8)], so that one K = 16 bf16 MMA yields sum_k a_lo*b_hi + a_hi*b_lo.
+// lo = v - trunc_tf32(v) (exact); rounding both factors to bf16 leaves a relative error of ~2^-20 in the product sum.
+__device__ __forceinline__ void cross_pack8(const float* v, float* out, bool first_lo) {
+    float lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float h; split_tf32(v[j], h, lo[j]); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t ph = pack_bf16x2(v[2 * j], v[2 * j + 1]), pl = pack_bf16x2(lo[2 * j], lo[2 * j + 1]);
+        out[j] = __uint_as_float(first_lo ? pl : ph);
+        out[4 + j] = __uint_as_float(first_lo ? ph : pl);
+    }
+}
+
 }  // namespace tc
 
 // ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ---------------------
@@ -189,7 +237,8 @@ typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, 
                                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // 3-D fp32 tensor [d2][d1][d0] (d0 innermost), row pitch / batch pitch in elements, box {b0, b1, 1}, SWIZZLE_128B.
 // Returns 0 on success.
-// atom32: 0 = CU_TENSOR_MAP_SWIZZLE_128B (K-major operands), 1 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32)
+// atom32: 0 = CU_TENSOR_MAP_SWIZZLE_128B (K-major operands), 1 = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32),
+//         2 = CU_TENSOR_MAP_SWIZZLE_NONE (tiles read by threads)
 int make_tensor_map_3d(CUtensorMap* out, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                        uint64_t pitch2, uint32_t b0, uint32_t b1, int atom32 = 0);
 

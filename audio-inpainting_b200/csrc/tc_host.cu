@@ -18,7 +18,8 @@ int make_tensor_map_3d(CUtensorMap* out, const float* base, uint64_t d0, uint64_
     const cuuint32_t box[3] = {b0, b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;

@@ -19,7 +19,7 @@ constexpr int PBK = 32;       // contraction elements per stage (one 128-byte sw
 template <int N>
 __global__ void __launch_bounds__(128)
 tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Kd, int mode,
-                int split, float* __restrict__ D, const float* __restrict__ Ag) {
+                int split, float* __restrict__ D, const float* __restrict__ Ag, const float* __restrict__ Bx) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_full, bar_mma;
     __shared__ uint32_t tmem_slot;
@@ -35,7 +35,7 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_init(&bar_mma, 1);
         mbar_fence_init();
     }
-    const uint32_t ncols = (mode == 2) ? 512 : (N < 32 ? 32 : N);
+    const uint32_t ncols = (mode >= 2) ? 512 : (N < 32 ? 32 : N);
     if (warp == 1) tmem_alloc(&tmem_slot, ncols);
     tcgen05_fence_before();
     __syncthreads();
@@ -44,7 +44,7 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bar_full, (uint32_t)stages * (a_bytes + b_bytes));
         for (int s = 0; s < stages; ++s) {
-            if (mode == 0 || mode == 2) {
+            if (mode == 0 || mode == 2 || mode == 3) {
                 tma_load_3d(sA + (size_t)s * PM * PBK, &mapA, &bar_full, s * PBK, 0, 0);
                 tma_load_3d(sB + (size_t)s * N * PBK, &mapB, &bar_full, s * PBK, 0, 0);
             } else {
@@ -56,10 +56,38 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     }
     mbar_wait(&bar_full, 0);
-    if (split) {       // generic-proxy rewrite of the tiles: hi in place, lo beside; then make it visible to the MMA
+    if (split && mode != 3) {       // generic-proxy rewrite of the tiles: hi in place, lo beside; then make it visible to the MMA
         const int na = stages * PM * PBK, nb = stages * N * PBK;
         for (int i = threadIdx.x; i < na; i += blockDim.x) { float h, l; split_tf32(sA[i], h, l); sA[i] = h; sAlo[i] = l; }
         for (int i = threadIdx.x; i < nb; i += blockDim.x) { float h, l; split_tf32(sB[i], h, l); sB[i] = h; sBlo[i] = l; }
+        fence_proxy_async_smem();
+    }
+    if (mode == 3) {
+        // A: raw tf32 at [N, N+Kd); packed bf16 cross operand at [N+Kd, N+2Kd): per group of 8 contraction elements,
+        // 8 columns = 16 bf16: elements 0-7 = A_lo, 8-15 = A_hi.  B cross tile: copied from Bx into sBlo in the
+        // SWIZZLE_128B K-major layout the TMA would produce (row n, 16-byte chunk c at (c ^ (n & 7))).
+        const int row = threadIdx.x;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + N;
+        for (int c0 = 0; c0 < Kd; c0 += 8) {
+            float hi[8], lo[8], px[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float v = Ag[(size_t)row * Kd + c0 + j]; float h; split_tf32(v, h, lo[j]); hi[j] = v; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                px[j] = __uint_as_float(pack_bf16x2(lo[2 * j], lo[2 * j + 1]));
+                px[4 + j] = __uint_as_float(pack_bf16x2(hi[2 * j], hi[2 * j + 1]));
+            }
+            tmem_st_32x8(tbase + c0, hi);
+            tmem_st_32x8(tbase + Kd + c0, px);
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+        for (int s = 0; s < stages; ++s)
+            for (int i = threadIdx.x; i < N * PBK; i += blockDim.x) {
+                const int n = i / PBK, k = i % PBK;
+                const int chunk = k >> 2;
+                sBlo[(size_t)s * N * PBK + n * PBK + ((chunk ^ (n & 7)) << 2) + (k & 3)] = Bx[(size_t)n * Kd + s * PBK + k];
+            }
         fence_proxy_async_smem();
     }
     if (mode == 2) {   // thread = row of A: raw values -> TMEM columns [N, N+Kd), residuals -> [N+Kd, N+2Kd)
@@ -82,6 +110,14 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         uint32_t acc = 0;
         for (int s = 0; s < stages; ++s) {
             for (int k8 = 0; k8 < PBK / 8; ++k8) {
+                if (mode == 3) {
+                    const uint64_t dbh = make_smem_desc(smem_u32(sB + (size_t)s * N * PBK) + k8 * 32, 16, 1024);
+                    const uint64_t dbx = make_smem_desc(smem_u32(sBlo + (size_t)s * N * PBK) + k8 * 32, 16, 1024);
+                    mma_tf32_ts(tmem, tmem + N + s * PBK + k8 * 8, dbh, idesc, acc);
+                    acc = 1;
+                    if (split) mma_bf16_ts(tmem, tmem + N + Kd + s * PBK + k8 * 8, dbx, make_idesc_bf16(PM, N, 0, 0), 1);
+                    continue;
+                }
                 const int passes = split ? 3 : 1;
                 for (int pss = 0; pss < passes; ++pss) {
                     const float* a = (pss == 2 ? sAlo : sA) + (size_t)s * PM * PBK;
@@ -124,12 +160,16 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
 }  // namespace ainmf
 
+extern "C" int ainmf_tc_probe_x(int mode, int split, int N, int Kd, const float* A, const float* B, const float* Bx, float* D, void* stream);
 extern "C" int ainmf_tc_probe(int mode, int split, int N, int Kd, const float* A, const float* B, float* D, void* stream) {
+    return ainmf_tc_probe_x(mode, split, N, Kd, A, B, nullptr, D, stream);
+}
+extern "C" int ainmf_tc_probe_x(int mode, int split, int N, int Kd, const float* A, const float* B, const float* Bx, float* D, void* stream) {
     using namespace ainmf;
     if ((N != 64 && N != 128) || Kd % PBK != 0 || Kd <= 0 || Kd > 128) return -1;
     CUtensorMap ma, mb;
     int rc;
-    if (mode == 0 || mode == 2) {
+    if (mode == 0 || mode == 2 || mode == 3) {
         rc = make_tensor_map_3d(&ma, A, Kd, PM, 1, Kd, (uint64_t)Kd * PM, PBK, PM);
         if (!rc) rc = make_tensor_map_3d(&mb, B, Kd, N, 1, Kd, (uint64_t)Kd * N, PBK, N);
     } else {
@@ -143,12 +183,72 @@ extern "C" int ainmf_tc_probe(int mode, int split, int N, int Kd, const float* A
     cudaError_t e;
     if (N == 64) {
         e = cudaFuncSetAttribute(tc_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_probe_kernel<64><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A);
+        if (e == cudaSuccess) tc_probe_kernel<64><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A, Bx);
     } else {
         e = cudaFuncSetAttribute(tc_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_probe_kernel<128><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A);
+        if (e == cudaSuccess) tc_probe_kernel<128><<<1, 128, smem, s>>>(ma, mb, Kd, mode, split, D, A, Bx);
     }
     if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+#endif
+
+// ---- MMA issue/throughput microbenchmark (diagnostic): `iters` groups of `per` back-to-back tcgen05.mma on garbage
+// operands, timed with clock64 from first issue to the commit's arrival.  ts = 1: A from TMEM, else from shared.
+#ifndef AINMF_EMU
+namespace ainmf {
+using namespace tc;
+__global__ void __launch_bounds__(128)
+tc_mma_bench_kernel(int N, int ts, int iters, int per, int commit_each, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(base)[i] = 1.0f;
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N, 0, 0);
+        const uint32_t idesc16 = make_idesc_bf16(128, N, 0, 0);
+        const uint64_t da = make_smem_desc(smem_u32(base), 16, 1024);
+        const uint64_t db = make_smem_desc(smem_u32(base) + 16384, 16, 1024);
+        uint32_t ph = 0;
+        const long long t0 = clock64();
+        long long t_issue = 0;
+        for (int it = 0; it < iters; ++it) {
+            for (int j = 0; j < per; ++j) {
+                const uint64_t o = (uint64_t)((j & 3) * 2);
+                if (ts == 1) mma_tf32_ts(tmem, tmem + 256 + (j & 3) * 8, db + o, idesc, 1);
+                else if (ts == 0) mma_tf32_ss(tmem, da + o, db + o, idesc, 1);
+                else if (ts == 3) mma_bf16_ts(tmem, tmem + 256 + (j & 3) * 8, db + o, idesc16, 1);
+                else mma_bf16_ss(tmem, da + o, db + o, idesc16, 1);
+            }
+            if (commit_each || it == iters - 1) {
+                if (it == iters - 1) t_issue = clock64() - t0;
+                mma_commit(&bar);
+                if (it == iters - 1 || commit_each == 2) { mbar_wait(&bar, ph); ph ^= 1; }
+            }
+        }
+        const long long t1 = clock64();
+        out[2 * blockIdx.x] = t1 - t0;
+        out[2 * blockIdx.x + 1] = t_issue;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+}  // namespace ainmf
+extern "C" int ainmf_tc_mma_bench(int N, int ts, int iters, int per, int commit_each, int blocks, long long* out, void* stream) {
+    using namespace ainmf;
+    cudaError_t e = cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    tc_mma_bench_kernel<<<blocks, 128, 50 * 1024, (cudaStream_t)stream>>>(N, ts, iters, per, commit_each, out);
     return (int)cudaGetLastError();
 }
 #endif
