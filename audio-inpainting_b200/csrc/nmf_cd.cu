@@ -12,6 +12,7 @@
 // The spectrogram is read exactly twice per iteration (xht_kernel, h_step_kernel): 8*F*T bytes.
 #include "kernels.h"
 #include "nmf_cd.cuh"
+#include "nmf_ts.cuh"
 
 #include <stdlib.h>
 
@@ -235,52 +236,202 @@ xht_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int
 }
 
 // =====================================================================================================
-// w sweep: B = sum_s partial[s]; W <- sweep(W, HHt, B); grid = (ceil(F / (256/L)), B)
+// W side of the iteration in one kernel; grid = (ceil(F/ROWS), B), 128 threads, a group of L lanes per row of W:
+//   B = sum_s partial[s] (fixed order);  g = W.G - B accumulated as rank-1 updates (rows of zeros are skipped);
+//   W <- sweep(W, G = HHt, B) in the incremental-gradient form: the whole gradient lives in registers, a coordinate
+//     step costs KP FMAs per row instead of a dot product, shuffles and the update logic on every lane;
+//   the new rows stay in shared memory and feed: the store of W; (tensor-core path) W^T and its bf16 cross operand
+//     for the H step's contraction (see tc::cross_pack8); the block's share of W^T W (register-tiled FFMA).
+//   The last block of a clip sums the Gram partials in block order (deterministic) and (tensor-core path) derives the
+//   H step's sweep operands from it (g_prep_block).
+// $SP/sklearn/decomposition/_nmf.py:379-396 (X.Ht, HHt -> W sweep), then :379-380 for the H half (W^T W).
 // =====================================================================================================
-template <int KP, int L>
-__global__ void __launch_bounds__(kThreads)
-w_sweep_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
-               const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
-               const ClipState* __restrict__ st) {
-    constexpr int SL = KP / L;
-    constexpr int ROWS = kThreads / L;
+template <int KP> struct WSideCfg {
+    static constexpr int L = (KP == 128) ? 2 : 1;
+    static constexpr int SL = KP / L;
+    static constexpr int THREADS = 128;
+    static constexpr int ROWS = THREADS / L;
+    static constexpr int GP = KP + 4 * L;                  // Gram row pitch (load_gram_padded<KP, L>)
+    static constexpr int AP = KP + 1;                      // row pitch of the W tile: odd, so rows and columns are conflict-free
+    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)KP * GP + KP + (size_t)ROWS * AP);
+};
+struct WSideTc {                      // outputs for the tensor-core H step; all null on the FFMA path
+    float* Wt; float* WtX; long long wt_stride; int ldw;
+    float* GX; float* blobs; float* scal;
+};
+template <int KP>
+__global__ void __launch_bounds__(128)
+w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
+              const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
+              float* __restrict__ gram_partial /*[B][gridDim.x][KP*KP]*/, float* __restrict__ WtW /*[B][KP*KP]*/,
+              unsigned* __restrict__ counters, WSideTc tc_out, const ClipState* __restrict__ st) {
+    using Cfg = WSideCfg<KP>;
+    constexpr int L = Cfg::L, SL = Cfg::SL, ROWS = Cfg::ROWS, GP = Cfg::GP, AP = Cfg::AP;
     AINMF_DYN_SMEM(smem_raw);
-    float* sG = reinterpret_cast<float*>(smem_raw);       // [KP][KP + 4L]
+    float* sG = reinterpret_cast<float*>(smem_raw);       // [KP][GP]
+    float* sInv = sG + KP * GP;                           // [KP]
+    float* sA = sInv + KP;                                // [ROWS][AP]
     __shared__ float s_red[32];
-    const int b = blockIdx.y;
+    __shared__ unsigned s_last;
+    const int b = blockIdx.y, P = gridDim.x;
     if (st[b].done) return;
-    load_gram_padded<KP, L>(sG, G + (long long)b * KP * KP);
-    const int l = threadIdx.x % L;
-    const int f = blockIdx.x * ROWS + threadIdx.x / L;
+    const float* Gb = G + (long long)b * KP * KP;
+    load_gram_padded<KP, L>(sG, Gb);
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) { const float d = Gb[t * KP + t]; sInv[t] = (d != 0.f) ? 1.0f / d : 0.f; }
+    const int l = threadIdx.x % L, r = threadIdx.x / L;
+    const int f0 = blockIdx.x * ROWS, f = f0 + r;
     const bool valid = f < F;
-    float a[SL], bv[SL];
+    float* ar = sA + r * AP;
+    float g[SL];
 #pragma unroll
-    for (int q = 0; q < SL; ++q) { a[q] = 0.f; bv[q] = 0.f; }
+    for (int q = 0; q < SL; ++q) g[q] = 0.f;
     if (valid) {
         const float* wr = W + (long long)b * w_stride + (long long)f * KP + l * SL;
 #pragma unroll
         for (int q = 0; q < SL; q += 4) {
             const float4 v = *reinterpret_cast<const float4*>(wr + q);
-            a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
+            ar[l * SL + q] = v.x; ar[l * SL + q + 1] = v.y; ar[l * SL + q + 2] = v.z; ar[l * SL + q + 3] = v.w;
         }
         for (int s = 0; s < S; ++s) {                      // fixed order -> deterministic
             const float* pr = partial + ((((long long)b * S + s) * F) + f) * KP + l * SL;
 #pragma unroll
             for (int q = 0; q < SL; q += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(pr + q);
-                bv[q] += v.x; bv[q + 1] += v.y; bv[q + 2] += v.z; bv[q + 3] += v.w;
+                g[q] -= v.x; g[q + 1] -= v.y; g[q + 2] -= v.z; g[q + 3] -= v.w;
             }
         }
+    } else {
+#pragma unroll
+        for (int q = 0; q < SL; ++q) ar[l * SL + q] = 0.f;
     }
     __syncthreads();
-    const float v = cd_sweep_row<KP, L>(a, bv, sG, l, valid);
-    if (valid) {
-        float* wr = W + (long long)b * w_stride + (long long)f * KP + l * SL;
+    const float* gl = sG + l * (SL + 4);
+    auto rank1 = [&](float c, int t) {                     // g[:] += c * G[t][this lane's slice]
+        const float* gr = gl + t * GP;
 #pragma unroll
-        for (int q = 0; q < SL; q += 4) *reinterpret_cast<float4*>(wr + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+        for (int q = 0; q < SL; q += 4) {
+            const float4 gv = *reinterpret_cast<const float4*>(gr + q);
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
+            const float2 cc = make_float2(c, c);
+            const float2 lo2 = __ffma2_rn(cc, make_float2(gv.x, gv.y), make_float2(g[q], g[q + 1]));
+            const float2 hi2 = __ffma2_rn(cc, make_float2(gv.z, gv.w), make_float2(g[q + 2], g[q + 3]));
+            g[q] = lo2.x; g[q + 1] = lo2.y; g[q + 2] = hi2.x; g[q + 3] = hi2.y;
+#else
+            g[q] = fmaf(c, gv.x, g[q]); g[q + 1] = fmaf(c, gv.y, g[q + 1]);
+            g[q + 2] = fmaf(c, gv.z, g[q + 2]); g[q + 3] = fmaf(c, gv.w, g[q + 3]);
+#endif
+        }
+    };
+    // gradient at the old W:  g = W.G - B  (G symmetric: row t of G scaled by W[row][t])
+#pragma unroll 4
+    for (int t = 0; t < KP; ++t) {
+        const float c = ar[t];
+        if (__ballot_sync(0xffffffffu, c != 0.f) == 0u) continue;       // warp-uniform
+        rank1(c, t);
     }
-    const float tot = block_sum(v, s_red);
-    if (threadIdx.x == 0) viol[(long long)b * gridDim.x + blockIdx.x] = tot;
+    // the sweep (reference order t = 0..KP-1); the lane that owns coordinate t decides, everybody applies the delta
+    float vsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < KP; ++t) {
+        const int o = t / SL, q = t % SL;
+        const float inv = sInv[t];
+        const float aq = ar[t];
+        const float grad = g[q];
+        const float pg = (aq == 0.f) ? fminf(0.f, grad) : grad;
+        const float an = fmaxf(fmaf(-grad, inv, aq), 0.f);
+        const bool own = (l == o) && valid;
+        const bool upd = own && (inv != 0.f);
+        vsum += own ? fabsf(pg) : 0.f;
+        float d = upd ? an - aq : 0.f;
+        if (upd) ar[t] = an;
+        if (L > 1) d = __shfl_sync(0xffffffffu, d, o, L);
+        if (__ballot_sync(0xffffffffu, d != 0.f) == 0u) continue;       // warp-uniform
+        rank1(d, t);
+    }
+    __syncthreads();
+
+    // ---- the new rows: W ------------------------------------------------------------------------------------------
+    const int rows_here = min(ROWS, F - f0);
+    float* Wb = W + (long long)b * w_stride + (long long)f0 * KP;
+    for (int i = threadIdx.x; i < rows_here * KP; i += blockDim.x) Wb[i] = sA[(i / KP) * AP + (i % KP)];
+#ifndef AINMF_EMU
+    if (tc_out.Wt) {
+        // Wt[k][f] = W[f][k] (tf32 main-term operand) and WtX, the bf16 cross operand with the same footprint: per group of
+        // 8 consecutive f, words 0-3 = pairs of bf16(w), words 4-7 = pairs of bf16(w - trunc_tf32(w))
+        float* Wt = tc_out.Wt + (long long)b * tc_out.wt_stride;
+        float* WtX = tc_out.WtX + (long long)b * tc_out.wt_stride;
+        for (int i = threadIdx.x; i < KP * ROWS; i += blockDim.x) {
+            const int k = i / ROWS, rr = i % ROWS, ff = f0 + rr;
+            if (ff >= tc_out.ldw) continue;
+            Wt[(long long)k * tc_out.ldw + ff] = sA[rr * AP + k];
+            const int g8 = rr & ~7, wd = rr & 7, e = 2 * (wd & 3);
+            const float v0 = sA[(g8 + e) * AP + k], v1 = sA[(g8 + e + 1) * AP + k];
+            uint32_t word;
+            if (wd < 4) word = tc::pack_bf16x2(v0, v1);
+            else { float h, l0, l1; tc::split_tf32(v0, h, l0); tc::split_tf32(v1, h, l1); word = tc::pack_bf16x2(l0, l1); }
+            WtX[(long long)k * tc_out.ldw + ff] = __uint_as_float(word);
+        }
+    }
+#endif
+    // ---- this block's share of W^T W: thread (ty, tx) of an 8 x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
+    {
+        constexpr int TI = KP / 8, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+        float* out = gram_partial + ((long long)b * P + blockIdx.x) * (KP * KP);
+#pragma unroll 1
+        for (int pass = 0; pass < PASSES; ++pass) {
+            float acc[TI][TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
+            const int c0 = pass * 16 * TJ + tx * TJ;
+#pragma unroll 2
+            for (int rr = 0; rr < ROWS; ++rr) {
+                const float* row = sA + rr * AP;
+                float fi[TI], fj[TJ];
+#pragma unroll
+                for (int i = 0; i < TI; ++i) fi[i] = row[ty * TI + i];
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) fj[j] = row[c0 + j];
+#pragma unroll
+                for (int i = 0; i < TI; ++i)
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) acc[i][j] = fmaf(fi[i], fj[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) out[(ty * TI + i) * KP + c0 + j] = acc[i][j];
+        }
+    }
+    const float tot = block_sum(vsum, s_red);
+    if (threadIdx.x == 0) viol[(long long)b * P + blockIdx.x] = tot;
+
+    // ---- last block of this clip: W^T W = sum of the partials in block order (deterministic) ---------------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == (unsigned)(P - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const float* pb = gram_partial + (long long)b * P * (KP * KP);
+        float* Go = WtW + (long long)b * (KP * KP);
+        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+            float sum = 0.f;
+            for (int q = 0; q < P; ++q) sum += pb[(long long)q * (KP * KP) + e];
+            Go[e] = sum;
+        }
+        if (threadIdx.x == 0) counters[b] = 0u;          // ready for the next launch
+#ifndef AINMF_EMU
+        if (tc_out.blobs) {
+            __syncthreads();                             // Go is read back below by other threads of this block
+            for (int blk = 0; blk < KP / 8; ++blk)
+                g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
+                             tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
+        }
+#endif
+    }
 }
 
 // =====================================================================================================
@@ -598,7 +749,6 @@ viol_sum_kernel(const float* __restrict__ v, int n, int B, double* __restrict__ 
 
 template <int KP>
 static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s) {
-    constexpr int LW = 8;
     cudaError_t e;
     const int fps = round_up(ceil_div(p.T, wk.xht_splits), 16);
     const int S = wk.use_tc ? wk.tc_splits : ceil_div(p.T, fps);
@@ -632,19 +782,19 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     }
     if (phases & NMF_PHASE_UPDATE) {
         {
-            const size_t smem = sizeof(float) * (size_t)KP * (KP + 4 * LW);
-            if ((e = cudaFuncSetAttribute(w_sweep_kernel<KP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-            auto kern = w_sweep_kernel<KP, LW>;
+            using WC = WSideCfg<KP>;
+            if ((e = cudaFuncSetAttribute(w_side_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::smem_bytes)) != cudaSuccess) return e;
+            auto kern = w_side_kernel<KP>;
+            WSideTc tco{nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr};
+            if (wk.use_tc) tco = WSideTc{wk.tc_Wt, wk.tc_WtLo, (long long)KP * p.ldf, p.ldf, wk.tc_GLo, wk.tc_blobs, wk.tc_scal};
             prof_begin(PROF_W_SWEEP, s);
-            AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(kThreads), smem, s, p.W, p.w_stride, p.F, wk.HHt,
-                         wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, p.state);
+            AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
+                         wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, wk.gram_partial,
+                         wk.WtW, wk.counters, tco, p.state);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             prof_end(PROF_W_SWEEP, s);
         }
-        // H half-step
-        prof_begin(PROF_GRAM_W, s);
-        if ((e = run_gram<KP>(p.W, p.w_stride, p.F, p.B, wk, wk.WtW, p.state, s)) != cudaSuccess) return e;
-        prof_end(PROF_GRAM_W, s);
+        // H half-step (W^T W came out of the W-side kernel)
         prof_begin(PROF_H_STEP, s);
         if (wk.use_tc) e = nmf_tc_hstep(p, wk, s);
         else if (wk.h_bm == 32) e = run_h_step<KP, 32>(p, wk, s);
@@ -868,7 +1018,7 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
     if (KP == 128 && bm == 128) bm = 64;                    // keeps two blocks per SM resident (smem)
     wk->h_bm = bm;
     wk->nH = ceil_div(T, bm);
-    wk->nW = ceil_div(F, kThreads / 8);
+    wk->nW = ceil_div(F, KP == 128 ? 64 : 128);            // rows per block of w_side_kernel (WSideCfg::ROWS)
     const int f_tiles = ceil_div(F, 128);
     long long splits = want / ((long long)B * f_tiles);
     if (splits < 1) splits = 1;
@@ -898,7 +1048,8 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
     size_t n = 0;
     n += al256(sizeof(float) * (size_t)B * KP * KP) * 2;                          // HHt, WtW
-    const int gp = wk.gram_max_blocks > wk.tc_splits ? wk.gram_max_blocks : wk.tc_splits;
+    int gp = wk.gram_max_blocks > wk.tc_splits ? wk.gram_max_blocks : wk.tc_splits;
+    if (wk.nW > gp) gp = wk.nW;
     const int xs = wk.xht_splits > wk.tc_splits ? wk.xht_splits : wk.tc_splits;
     n += al256(sizeof(float) * (size_t)B * gp * KP * KP);                          // gram partials
     n += al256(sizeof(unsigned) * (size_t)B);                                      // counters
@@ -915,7 +1066,8 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
     auto take = [&](size_t bytes) { char* r = p; p += al256(bytes); return r; };
     wk->HHt = (float*)take(sizeof(float) * (size_t)B * KP * KP);
     wk->WtW = (float*)take(sizeof(float) * (size_t)B * KP * KP);
-    const int gp = wk->gram_max_blocks > wk->tc_splits ? wk->gram_max_blocks : wk->tc_splits;
+    int gp = wk->gram_max_blocks > wk->tc_splits ? wk->gram_max_blocks : wk->tc_splits;
+    if (wk->nW > gp) gp = wk->nW;
     const int xs = wk->xht_splits > wk->tc_splits ? wk->xht_splits : wk->tc_splits;
     wk->gram_partial = (float*)take(sizeof(float) * (size_t)B * gp * KP * KP);
     wk->counters = (unsigned*)take(sizeof(unsigned) * (size_t)B);

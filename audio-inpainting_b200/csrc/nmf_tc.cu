@@ -13,37 +13,6 @@ using namespace tc;
 constexpr int TC_BK = 32;          // contraction elements per stage (one 128-byte row)
 constexpr int TC_M = 128;          // MMA M
 
-// Wt[b][k][f] = W[b][f][k] (the tf32 main-term operand: the tensor core ignores the low 13 mantissa bits) and WtX, the
-// bf16 cross-term operand with the same footprint: per group of 8 consecutive f, 16 bf16 = [bf16(w)(8) | bf16(w_lo)(8)],
-// w_lo = w - trunc_tf32(w)  (see tc::cross_pack8).  32x32 tiles; grid = (ceil(F/32), KP/32, B)
-__global__ void __launch_bounds__(kThreads)
-wt_split_kernel(const float* __restrict__ W, long long w_stride, int F, int KP, int ldw, float* __restrict__ Wt,
-                float* __restrict__ WtX, long long wt_stride, const ClipState* __restrict__ st) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    if (st[b].done) return;
-    const int f0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    for (int r = ly; r < 32; r += 8) {
-        const int f = f0 + r;
-        tile[r][lx] = (f < F) ? W[(long long)b * w_stride + (long long)f * KP + k0 + lx] : 0.f;
-    }
-    __syncthreads();
-    for (int r = ly; r < 32; r += 8) {
-        const int k = k0 + r, f = f0 + lx;
-        if (f < ldw) {
-            Wt[(long long)b * wt_stride + (long long)k * ldw + f] = tile[lx][r];
-            // word (lx & 7) of the group of 8: words 0-3 = pairs of bf16(w), words 4-7 = pairs of bf16(w_lo)
-            const int g = lx & ~7, wd = lx & 7, e = 2 * (wd & 3);
-            const float v0 = tile[g + e][r], v1 = tile[g + e + 1][r];
-            uint32_t word;
-            if (wd < 4) word = pack_bf16x2(v0, v1);
-            else { float h, l0, l1; split_tf32(v0, h, l0); split_tf32(v1, h, l1); word = pack_bf16x2(l0, l1); }
-            WtX[(long long)b * wt_stride + (long long)k * ldw + f] = __uint_as_float(word);
-        }
-    }
-}
-
 // out[b][e] = sum_s partial[b][s][e]  (fixed order); grid = (ceil(n4/256), B)
 __global__ void __launch_bounds__(kThreads)
 reduce_splits_kernel(const float* __restrict__ partial, int S, long long n4, float* __restrict__ out, long long out_stride,
@@ -75,15 +44,9 @@ cudaError_t nmf_tc_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s)
     return cudaGetLastError();
 }
 
-// H half-step: W^T operands for the contraction, then the persistent TMEM-operand kernel (nmf_ts.cu)
-cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
-    const int ldw = p.ldf, KP = p.KP;
-    AINMF_LAUNCH(wt_split_kernel, dim3(ceil_div(ldw, 32), KP / 32, p.B), dim3(kThreads), 0, s, p.W, p.w_stride, p.F, KP, ldw,
-                 wk.tc_Wt, wk.tc_WtLo, (long long)KP * ldw, p.state);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return nmf_ts_hstep(p, wk, s);
-}
+// H half-step: the persistent TMEM-operand kernel (nmf_ts.cu); its W^T operands and the operands derived from W^T W are
+// written by the W-side kernel (nmf_cd.cu: w_side_kernel)
+cudaError_t nmf_tc_hstep(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) { return nmf_ts_hstep(p, wk, s); }
 
 int nmf_tc_setup(const NmfProblem& p, NmfWork* wk, TcMaps* m) {
     if (!wk->use_tc) return 0;

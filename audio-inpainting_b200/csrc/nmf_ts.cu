@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "tc.cuh"
+#include "nmf_ts.cuh"
 
 #ifndef AINMF_EMU
 namespace ainmf {
@@ -40,7 +41,6 @@ constexpr int TS_BK = 32;            // contraction elements per stage (one 128-
 constexpr int TS_M = 128;            // frames per tile = MMA M = TMEM lanes
 constexpr int TS_THREADS = 384;
 constexpr int TS_QD = 2;             // contraction chunks allowed in the tensor pipe at once (bounds the latency of a sweep update)
-constexpr int TS_SC = 136;           // floats of sweep scalars per block: G diagonal block 8x8, look-ahead block 8x8, 1/diag
 
 template <int KP> struct TsCfg {
     static constexpr int NSS = (KP == 64) ? 6 : 4;               // shared-memory stages (X chunk + W^T hi/lo chunk)
@@ -669,50 +669,6 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
 }
 
 
-// Per clip and per block of 8 coordinates:
-//   blobs: the rows G[8blk .. 8blk+8)[0..KP) of the Gram matrix laid out as the K-major (no swizzle) [N = KP][K = 8]
-//          operand of the sweep update -- raw values (tf32 main term), then the bf16 cross operand;
-//   scal : what the sweep threads read themselves: the diagonal block G[8blk+j][8blk+i], the look-ahead block
-//          G[8blk+i][8(blk+1)+c] and the reciprocals of the block's diagonal (0 where the diagonal is 0);
-//   Glo (GX): the bf16 cross operand of G's rows for the contraction's Ht.G chunks (same footprint as G).
-// grid = (KP/8, B)
-__global__ void __launch_bounds__(kThreads)
-g_prep_kernel(const float* __restrict__ G, float* __restrict__ Glo, float* __restrict__ blobs, float* __restrict__ scal, int KP,
-              const ClipState* __restrict__ st) {
-    const int b = blockIdx.y, blk = blockIdx.x, nblk = KP / 8;
-    if (st[b].done) return;
-    const float* Gb = G + (long long)b * KP * KP;
-    float* blob = blobs + ((long long)b * nblk + blk) * (16 * KP);
-    float* sc = scal + ((long long)b * nblk + blk) * TS_SC;
-    for (int idx = threadIdx.x; idx < 8 * KP; idx += blockDim.x) {
-        const int j = idx / KP, n = idx - j * KP;
-        const float v = Gb[(8 * blk + j) * KP + n];
-        blob[((j >> 2) * KP + n) * 4 + (j & 3)] = v;
-    }
-    // cross operands (tc::cross_pack8, B-side order [hi(8) | lo(8)]): rows n of the [N = KP][K = 16 bf16] update operand
-    // (two 8-element cores, KP*16 bytes apart) and the same 8 words as columns 8blk..8blk+7 of row n of GX
-    for (int n = threadIdx.x; n < KP; n += blockDim.x) {
-        float v[8], w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = Gb[(8 * blk + j) * KP + n];          // G[8blk+j][n] = G[n][8blk+j]
-        cross_pack8(v, w, false);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            blob[8 * KP + ((j >> 2) * KP + n) * 4 + (j & 3)] = w[j];
-            Glo[(long long)b * KP * KP + n * KP + 8 * blk + j] = w[j];
-        }
-    }
-    if (threadIdx.x < 64) {
-        const int j = threadIdx.x >> 3, i = threadIdx.x & 7;
-        sc[8 * j + i] = Gb[(8 * blk + j) * KP + 8 * blk + i];
-        sc[64 + 8 * j + i] = (blk + 1 < nblk) ? Gb[(8 * blk + j) * KP + 8 * (blk + 1) + i] : 0.f;
-    }
-    if (threadIdx.x < 8) {
-        const float d = Gb[(8 * blk + threadIdx.x) * (KP + 1)];
-        sc[128 + threadIdx.x] = (d != 0.f) ? 1.0f / d : 0.f;
-    }
-}
-
 static inline const CUtensorMap& as_map(const TcMapBlob& b) { return *reinterpret_cast<const CUtensorMap*>(&b); }
 
 template <int KP>
@@ -730,8 +686,6 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
         if ((e = cudaFuncSetAttribute(h_step_ts_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)) != cudaSuccess) return e;
         attr_set = true;
     }
-    AINMF_LAUNCH(g_prep_kernel, dim3(KP / 8, p.B), dim3(kThreads), 0, s, wk.WtW, wk.tc_GLo, wk.tc_blobs, wk.tc_scal, KP, p.state);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     static int exp_flags = -1;
     if (exp_flags < 0) { const char* x_ = getenv("AINMF_TS_EXP"); exp_flags = x_ ? atoi(x_) : 0; }
     static long long* dbg = nullptr;
