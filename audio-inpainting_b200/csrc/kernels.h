@@ -134,7 +134,7 @@ struct alignas(64) TcMapBlob { unsigned char b[128]; };
 struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXs, mapHs, mapHmn, mapHk, mapG, mapGlo; };
 
 struct NmfWork {
-    int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64;
+    int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64, w_lanes = 1, w_rows = 128;
     // tensor-core path (tcgen05, error-compensated TF32) for the two V-sized contractions; KP in {64,128}
     int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
     float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed, and its TF32 residual

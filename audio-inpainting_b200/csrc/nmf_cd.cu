@@ -242,44 +242,109 @@ xht_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int
 //     step costs KP FMAs per row instead of a dot product, shuffles and the update logic on every lane;
 //   the new rows stay in shared memory and feed: the store of W; (tensor-core path) W^T and its bf16 cross operand
 //     for the H step's contraction (see tc::cross_pack8); the block's share of W^T W (register-tiled FFMA).
-//   The last block of a clip sums the Gram partials in block order (deterministic) and (tensor-core path) derives the
-//   H step's sweep operands from it (g_prep_block).
+//   w_finish_kernel then sums the Gram partials in block order (deterministic) and (tensor-core path) derives the
+//   H step's sweep operands from them (g_prep_block).
 // $SP/sklearn/decomposition/_nmf.py:379-396 (X.Ht, HHt -> W sweep), then :379-380 for the H half (W^T W).
 // =====================================================================================================
-template <int KP> struct WSideCfg {
-    static constexpr int L = (KP == 128) ? 2 : 1;
-    static constexpr int SL = KP / L;
-    static constexpr int THREADS = 128;
-    static constexpr int ROWS = THREADS / L;
+template <int KP, int L_, int ROWS_> struct WSideCfg {
+    static constexpr int L = L_;                           // lanes per row: 1 for big batches (fewest instructions), up to 8 when
+    static constexpr int SL = KP / L;                      // few rows must fill the machine (shorter serial chain per lane)
+    static constexpr int ROWS = ROWS_;                     // rows per block: 128, or 32 (with the most lanes) for a single clip
+    static constexpr int THREADS = ROWS * L;
+    static_assert(SL >= 4 && SL <= 64 && THREADS / 16 <= KP && THREADS >= 128, "lanes per row");
     static constexpr int GP = KP + 4 * L;                  // Gram row pitch (load_gram_padded<KP, L>)
-    static constexpr int AP = KP + 1;                      // row pitch of the W tile: odd, so rows and columns are conflict-free
+    static constexpr int AP = KP + 4;                      // row pitch of the W tile (16-byte aligned rows)
     static constexpr size_t smem_bytes = sizeof(float) * ((size_t)KP * GP + KP + (size_t)ROWS * AP);
 };
 struct WSideTc {                      // outputs for the tensor-core H step; all null on the FFMA path
     float* Wt; float* WtX; long long wt_stride; int ldw;
     float* GX; float* blobs; float* scal;
 };
-template <int KP>
-__global__ void __launch_bounds__(128)
+template <int KP, int LANES, int NROWS>
+__global__ void __launch_bounds__(NROWS * LANES)
 w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
               const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
-              float* __restrict__ gram_partial /*[B][gridDim.x][KP*KP]*/, float* __restrict__ WtW /*[B][KP*KP]*/,
-              unsigned* __restrict__ counters, WSideTc tc_out, const ClipState* __restrict__ st) {
-    using Cfg = WSideCfg<KP>;
+              float* __restrict__ gram_partial /*[B][gridDim.x][KP*KP]*/, WSideTc tc_out, const ClipState* __restrict__ st) {
+    using Cfg = WSideCfg<KP, LANES, NROWS>;
     constexpr int L = Cfg::L, SL = Cfg::SL, ROWS = Cfg::ROWS, GP = Cfg::GP, AP = Cfg::AP;
     AINMF_DYN_SMEM(smem_raw);
     float* sG = reinterpret_cast<float*>(smem_raw);       // [KP][GP]
     float* sInv = sG + KP * GP;                           // [KP]
     float* sA = sInv + KP;                                // [ROWS][AP]
     __shared__ float s_red[32];
-    __shared__ unsigned s_last;
     const int b = blockIdx.y, P = gridDim.x;
     if (st[b].done) return;
     const float* Gb = G + (long long)b * KP * KP;
     load_gram_padded<KP, L>(sG, Gb);
     for (int t = threadIdx.x; t < KP; t += blockDim.x) { const float d = Gb[t * KP + t]; sInv[t] = (d != 0.f) ? 1.0f / d : 0.f; }
+    const int f0 = blockIdx.x * ROWS;
+    float vsum = 0.f;
+    if constexpr (L == 1) {
+        // One thread per row, the reference's own formulation (_cdnmf_fast.pyx:8-38): the gradient of coordinate t is a dot
+        // product of the row (registers) with row t of G (shared, packed FFMA2, four chains); nothing is updated
+        // incrementally -- K^2 FMAs per row instead of the 2 K^2 of the rank-1 form.  -B waits in the row's slot of the
+        // shared tile, which receives the new row afterwards.
+        const int r = threadIdx.x;
+        const int f = f0 + r;
+        const bool valid = f < F;
+        float* ar = sA + r * AP;
+        {
+            float4 nb[KP / 4];
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) nb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                for (int s = 0; s < S; ++s) {              // fixed order -> deterministic
+                    const float* pr = partial + ((((long long)b * S + s) * F) + f) * KP;
+#pragma unroll
+                    for (int q = 0; q < KP / 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4*>(pr + 4 * q);
+                        nb[q].x -= v.x; nb[q].y -= v.y; nb[q].z -= v.z; nb[q].w -= v.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) *reinterpret_cast<float4*>(ar + 4 * q) = nb[q];
+        }
+        float a[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) a[q] = 0.f;
+        if (valid) {
+            const float* wr = W + (long long)b * w_stride + (long long)f * KP;
+#pragma unroll
+            for (int q = 0; q < KP; q += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(wr + q);
+                a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < KP; ++t) {
+            const float* gr = sG + t * GP;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int q = 0; q < KP; q += 4) {
+                const float4 gv = *reinterpret_cast<const float4*>(gr + q);
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
+                const float2 p0 = __ffma2_rn(make_float2(a[q], a[q + 1]), make_float2(gv.x, gv.y), make_float2(d0, d1));
+                const float2 p1 = __ffma2_rn(make_float2(a[q + 2], a[q + 3]), make_float2(gv.z, gv.w), make_float2(d2, d3));
+                d0 = p0.x; d1 = p0.y; d2 = p1.x; d3 = p1.y;
+#else
+                d0 = fmaf(a[q], gv.x, d0); d1 = fmaf(a[q + 1], gv.y, d1);
+                d2 = fmaf(a[q + 2], gv.z, d2); d3 = fmaf(a[q + 3], gv.w, d3);
+#endif
+            }
+            const float grad = ((d0 + d1) + (d2 + d3)) + ar[t];
+            const float inv = sInv[t];
+            const float aq = a[t];
+            const float pg = (aq == 0.f) ? fminf(0.f, grad) : grad;
+            vsum += valid ? fabsf(pg) : 0.f;
+            if (valid && inv != 0.f) a[t] = fmaxf(fmaf(-grad, inv, aq), 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < KP; q += 4) *reinterpret_cast<float4*>(ar + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+    } else {
     const int l = threadIdx.x % L, r = threadIdx.x / L;
-    const int f0 = blockIdx.x * ROWS, f = f0 + r;
+    const int f = f0 + r;
     const bool valid = f < F;
     float* ar = sA + r * AP;
     float g[SL];
@@ -330,7 +395,6 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         rank1(c, t);
     }
     // the sweep (reference order t = 0..KP-1); the lane that owns coordinate t decides, everybody applies the delta
-    float vsum = 0.f;
 #pragma unroll
     for (int t = 0; t < KP; ++t) {
         const int o = t / SL, q = t % SL;
@@ -348,12 +412,14 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         if (__ballot_sync(0xffffffffu, d != 0.f) == 0u) continue;       // warp-uniform
         rank1(d, t);
     }
+    }
     __syncthreads();
 
     // ---- the new rows: W ------------------------------------------------------------------------------------------
     const int rows_here = min(ROWS, F - f0);
     float* Wb = W + (long long)b * w_stride + (long long)f0 * KP;
-    for (int i = threadIdx.x; i < rows_here * KP; i += blockDim.x) Wb[i] = sA[(i / KP) * AP + (i % KP)];
+    for (int i = threadIdx.x; i < rows_here * KP / 4; i += blockDim.x)
+        *reinterpret_cast<float4*>(Wb + 4 * i) = *reinterpret_cast<const float4*>(sA + ((4 * i) / KP) * AP + ((4 * i) % KP));
 #ifndef AINMF_EMU
     if (tc_out.Wt) {
         // Wt[k][f] = W[f][k] (tf32 main-term operand) and WtX, the bf16 cross operand with the same footprint: per group of
@@ -373,9 +439,9 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         }
     }
 #endif
-    // ---- this block's share of W^T W: thread (ty, tx) of an 8 x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
+    // ---- this block's share of W^T W: thread (ty, tx) of a (THREADS/16) x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
     {
-        constexpr int TI = KP / 8, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
+        constexpr int TY = Cfg::THREADS / 16, TI = KP / TY, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
         const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
         float* out = gram_partial + ((long long)b * P + blockIdx.x) * (KP * KP);
 #pragma unroll 1
@@ -390,10 +456,23 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
             for (int rr = 0; rr < ROWS; ++rr) {
                 const float* row = sA + rr * AP;
                 float fi[TI], fj[TJ];
+                if constexpr (TI % 4 == 0) {
 #pragma unroll
-                for (int i = 0; i < TI; ++i) fi[i] = row[ty * TI + i];
+                    for (int i = 0; i < TI; i += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(row + ty * TI + i);
+                        fi[i] = v.x; fi[i + 1] = v.y; fi[i + 2] = v.z; fi[i + 3] = v.w;
+                    }
+                } else {
 #pragma unroll
-                for (int j = 0; j < TJ; ++j) fj[j] = row[c0 + j];
+                    for (int i = 0; i < TI; ++i) fi[i] = row[ty * TI + i];
+                }
+                if constexpr (TJ == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + c0);
+                    fj[0] = v.x; fj[1] = v.y; fj[2] = v.z; fj[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) fj[j] = row[c0 + j];
+                }
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
@@ -408,30 +487,29 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
     const float tot = block_sum(vsum, s_red);
     if (threadIdx.x == 0) viol[(long long)b * P + blockIdx.x] = tot;
 
-    // ---- last block of this clip: W^T W = sum of the partials in block order (deterministic) ---------------------
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == (unsigned)(P - 1)) ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        const float* pb = gram_partial + (long long)b * P * (KP * KP);
-        float* Go = WtW + (long long)b * (KP * KP);
-        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
-            float sum = 0.f;
-            for (int q = 0; q < P; ++q) sum += pb[(long long)q * (KP * KP) + e];
-            Go[e] = sum;
-        }
-        if (threadIdx.x == 0) counters[b] = 0u;          // ready for the next launch
-#ifndef AINMF_EMU
-        if (tc_out.blobs) {
-            __syncthreads();                             // Go is read back below by other threads of this block
-            for (int blk = 0; blk < KP / 8; ++blk)
-                g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
-                             tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
-        }
-#endif
+}
+
+// W^T W = sum of the W-side kernel's partials in block order (deterministic), 8 rows per block, and (tensor-core path) the
+// H step's operands that derive from those 8 rows (g_prep_block); grid = (KP/8, B)
+__global__ void __launch_bounds__(kThreads)
+w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P, int KP, float* __restrict__ WtW, WSideTc tc_out,
+                const ClipState* __restrict__ st) {
+    const int b = blockIdx.y, blk = blockIdx.x;
+    if (st[b].done) return;
+    const float* pb = gram_partial + (long long)b * P * (KP * KP) + 8 * blk * KP;
+    float* Go = WtW + (long long)b * (KP * KP);
+    for (int e = threadIdx.x; e < 8 * KP; e += blockDim.x) {
+        float sum = 0.f;
+        for (int q = 0; q < P; ++q) sum += pb[(long long)q * (KP * KP) + e];
+        Go[8 * blk * KP + e] = sum;
     }
+#ifndef AINMF_EMU
+    if (tc_out.blobs) {
+        __syncthreads();                                 // the rows just written are read back by other threads of the block
+        g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
+                     tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
+    }
+#endif
 }
 
 // =====================================================================================================
@@ -782,15 +860,28 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     }
     if (phases & NMF_PHASE_UPDATE) {
         {
-            using WC = WSideCfg<KP>;
-            if ((e = cudaFuncSetAttribute(w_side_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::smem_bytes)) != cudaSuccess) return e;
-            auto kern = w_side_kernel<KP>;
             WSideTc tco{nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr};
             if (wk.use_tc) tco = WSideTc{wk.tc_Wt, wk.tc_WtLo, (long long)KP * p.ldf, p.ldf, wk.tc_GLo, wk.tc_blobs, wk.tc_scal};
             prof_begin(PROF_W_SWEEP, s);
-            AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
-                         wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, wk.gram_partial,
-                         wk.WtW, wk.counters, tco, p.state);
+            auto launch = [&](auto cfg) -> cudaError_t {
+                using WC = decltype(cfg);
+                auto kern = w_side_kernel<KP, WC::L, WC::ROWS>;
+                cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::smem_bytes);
+                if (e2 != cudaSuccess) return e2;
+                AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
+                             wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, wk.gram_partial,
+                             tco, p.state);
+                return cudaGetLastError();
+            };
+            constexpr int LMIN = (KP == 128) ? 2 : 1, LMAX = (KP == 32) ? 4 : 8;
+            int lanes = wk.w_lanes < LMIN ? LMIN : (wk.w_lanes > LMAX ? LMAX : wk.w_lanes);
+            if (wk.w_rows == 32) e = launch(WSideCfg<KP, LMAX, 32>{});
+            else if (lanes >= 8) { if constexpr (LMAX >= 8) e = launch(WSideCfg<KP, 8, 128>{}); }
+            else if (lanes >= 4) e = launch(WSideCfg<KP, 4, 128>{});
+            else if (lanes >= 2) e = launch(WSideCfg<KP, 2, 128>{});
+            else { if constexpr (LMIN <= 1) e = launch(WSideCfg<KP, 1, 128>{}); }
+            if (e != cudaSuccess) return e;
+            AINMF_LAUNCH(w_finish_kernel, dim3(KP / 8, p.B), dim3(kThreads), 0, s, wk.gram_partial, wk.nW, KP, wk.WtW, tco, p.state);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             prof_end(PROF_W_SWEEP, s);
         }
@@ -1018,7 +1109,16 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
     if (KP == 128 && bm == 128) bm = 64;                    // keeps two blocks per SM resident (smem)
     wk->h_bm = bm;
     wk->nH = ceil_div(T, bm);
-    wk->nW = ceil_div(F, KP == 128 ? 64 : 128);            // rows per block of w_side_kernel (WSideCfg::ROWS)
+    {   // W-side kernel shape: 128 rows per block and as few lanes per row as still give the machine about 8 warps per
+        // SM; when even 8 lanes leave most SMs idle (one long signal), 32-row blocks with the most lanes
+        wk->w_rows = 128;
+        wk->nW = ceil_div(F, 128);
+        const long long blocks = (long long)B * wk->nW;
+        int lanes = 1;
+        while (lanes < 8 && blocks * 4 * lanes < 8LL * n_sm) lanes *= 2;
+        wk->w_lanes = lanes;
+        if (lanes == 8 && blocks * 2 < n_sm) { wk->w_rows = 32; wk->nW = ceil_div(F, 32); }
+    }
     const int f_tiles = ceil_div(F, 128);
     long long splits = want / ((long long)B * f_tiles);
     if (splits < 1) splits = 1;

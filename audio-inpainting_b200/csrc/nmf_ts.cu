@@ -171,6 +171,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 0), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
             const uint32_t neg = 1u << 13;                            // negate A
+            const int tail8 = (F - (nkX - 1) * TS_BK + 7) / 8;
             uint32_t it = 0, tl = 0;
             while (tiles.next(b, mt)) {
                 const uint32_t buf = tl & 1;
@@ -188,8 +189,10 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     const uint64_t d_bh = make_smem_desc(smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::X_BYTES), 16, 1024);
                     const uint64_t d_bl = d_bh + (uint64_t)(Cfg::B_BYTES >> 4);
                     const uint32_t acol = tmem + Cfg::COL_A + a * 64;
+                    const int n8 = (i == nkX - 1) ? tail8 : TS_BK / 8;      // the last X chunk may hold fewer than 32 bins
 #pragma unroll
                     for (int k8 = 0; k8 < TS_BK / 8; ++k8) {
+                        if (k8 >= n8) break;
                         const uint64_t o = (uint64_t)(k8 * 32 >> 4);
                         mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, idesc | ng, (i > 0 || k8 > 0) ? 1u : 0u);
                         mma_bf16_ts(dcol, acol + 32 + k8 * 8, d_bl + o, idesc16 | ng, 1);

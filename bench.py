@@ -303,7 +303,7 @@ def run_c5(args, rank, local_rank, world):
     torch.cuda.synchronize()
     pms, pcn = (C.c_double * 6)(), (C.c_int64 * 6)()
     L.ainmf_profile(h, 0, pms, pcn)
-    names = ["gram_Ht", "xht_partial", "w_sweep", "gram_W", "h_step_fused", "stop_rule"]
+    names = ["gram_Ht", "xht_gram_tc", "w_side_fused", "gram_W", "h_step_tc", "stop_rule"]
     kern_ms = {k: float(pms[i]) for i, k in enumerate(names)}
     n_it = max(int(pcn[4]), 1)
     iter_ms = sum(kern_ms.values()) / n_it          # this rank's kernels; the all-reduce sits between them
@@ -451,7 +451,7 @@ def main():
     pms = (C.c_double * 6)()
     pcn = (C.c_int64 * 6)()
     L.ainmf_profile(h, 0, pms, pcn)
-    kern_names = ["gram_Ht", "xht_partial", "w_sweep", "gram_W", "h_step_fused", "stop_rule"]
+    kern_names = ["gram_Ht", "xht_gram_tc", "w_side_fused", "gram_W", "h_step_tc", "stop_rule"]
     kern_ms = {k: float(pms[i]) for i, k in enumerate(kern_names)}
     n_it = max(int(pcn[4]), 1)
     iter_ms = sum(kern_ms.values()) / n_it
@@ -459,11 +459,14 @@ def main():
     bytes_iter = alg_bytes_per_iter(F, T, K) * B
     achieved = bytes_iter / (iter_ms * 1e-3) / 1e9
     # per-kernel algorithmic bytes (float32): what each launch must move at least
-    kb = {"gram_Ht": 4.0 * T * K + 4.0 * K * K, "xht_partial": 4.0 * F * T + 4.0 * T * K + 4.0 * F * K,
-          "w_sweep": 12.0 * F * K + 4.0 * K * K, "gram_W": 4.0 * F * K + 4.0 * K * K,
-          "h_step_fused": 4.0 * F * T + 4.0 * F * K + 8.0 * T * K + 4.0 * K * K, "stop_rule": 0.0}
+    # (gram_Ht / gram_W are separate launches only on the FFMA path, K < 64: on the tensor-core path the Gram of Ht comes
+    # out of the X.Ht kernel and W^T W out of the fused W-side kernel, so their entries read 0)
+    kb = {"gram_Ht": 4.0 * T * K + 4.0 * K * K, "xht_gram_tc": 4.0 * F * T + 4.0 * T * K + 4.0 * F * K,
+          "w_side_fused": 12.0 * F * K + 8.0 * K * K, "gram_W": 4.0 * F * K + 4.0 * K * K,
+          "h_step_tc": 4.0 * F * T + 4.0 * F * K + 8.0 * T * K + 4.0 * K * K, "stop_rule": 0.0}
     kernels = {k: {"ms_per_launch": kern_ms[k] / n_it, "share": kern_ms[k] / max(sum(kern_ms.values()), 1e-12),
-                   "hbm_frac": (kb[k] * B / max(kern_ms[k] / n_it * 1e-3, 1e-12) / 1e9) / peak} for k in kern_names}
+                   "hbm_frac": ((kb[k] * B / (kern_ms[k] / n_it * 1e-3) / 1e9) / peak) if kern_ms[k] > 0 else None}
+               for k in kern_names}
 
     # ---- end-to-end leg through the C ABI with HOST buffers -----------------------------------------
     xh = torch.empty((B, N), dtype=torch.float32).pin_memory()
@@ -539,7 +542,7 @@ def main():
                 "ms_per_step": float(e2e_ms[0]) / args.steps, "api": "ainmf_inpaint_host (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "CD-NMF iteration (gram, X.Ht, W sweep, gram, fused X^T.W+H sweep, stop)",
+        "roofline": {"bound": "hbm", "kernel": "CD-NMF iteration = xht_ts_kernel (X.Ht + Gram, tcgen05) + w_side_kernel (W sweep, W^T W, operands) + h_step_ts_kernel (X^T.W + H sweep, tcgen05) + stop_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_iteration": bytes_iter, "ms_per_iteration": iter_ms,
                      "kernels": kernels},
