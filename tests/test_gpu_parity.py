@@ -151,6 +151,21 @@ def test_nmf_fit_matches_sklearn_custom_init(ops, F, T, K, iters):
     assert rel_l2(W[0].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 1e-3
 
 
+@pytest.mark.parametrize("B,F,T,K,iters", [(160, 257, 130, 64, 6), (40, 257, 200, 64, 6), (12, 513, 140, 40, 6), (3, 200, 260, 128, 5),
+                                           (70, 129, 150, 20, 6), (60, 257, 130, 64, 5)])
+def test_nmf_fit_batch_shapes_of_the_w_side_kernel(ops, B, F, T, K, iters):
+    """The W-side kernel picks lanes per row / rows per block from the batch size (one thread per row for big batches, up
+    to 8 lanes in 32-row blocks for a single clip); every shape must agree with sklearn on the same inputs."""
+    rng = np.random.default_rng(B * 1000 + F)
+    X = np.abs(rng.standard_normal((B, F, T))).astype(np.float32)
+    W, H, err, nit = ops.nmf_fit(dev(X), K, iters, 0.0, 3, None, None)
+    for b in sorted({0, B // 2, B - 1}):
+        Wo, Ho, no, eo = libcalls.nmf_fit(X[b], K, seed=3, max_iter=iters, tol=0.0)
+        assert int(nit[b]) == no == iters
+        assert abs(float(err[b]) - eo) <= 1e-4 * eo
+        assert rel_l2(W[b].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[b].cpu().numpy(), Ho) < 1e-3
+
+
 def test_nmf_fit_seeded_init_and_early_stop(ops):
     """init='random' with random_state: same initial factors as sklearn, same stop iteration (+-1)."""
     rng = np.random.default_rng(11)
