@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "comm.cu", "stft.cu", "mask.cu", "impute.cu", "nmf_cd.cu", "pcm.cu", "tc_host.cu", "tc_probe.cu", "nmf_tc.cu", "nmf_ts.cu", "sweep_test.cu"]
+SOURCES = ["api.cu", "comm.cu", "stft.cu", "mask.cu", "impute.cu", "nmf_cd.cu", "pcm.cu", "gaps.cu", "tc_host.cu", "tc_probe.cu", "nmf_tc.cu", "nmf_ts.cu", "sweep_test.cu"]
 LIB = os.path.join(HERE, "libainmf.so")
 EMU_LIB = os.path.join(ROOT, "tests", "_emu", "libainmf_emu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

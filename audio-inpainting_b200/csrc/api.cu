@@ -725,6 +725,74 @@ int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pc
     return AINMF_OK;
 }
 
+// ---- sample-level detectors / baselines of the sibling scripts, Part-0 post-processing ----------
+int ainmf_find_main_gap(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, int64_t* span,
+                        void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || !span || batch <= 0 || n_samples < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_find_main_gap");
+    CU(h, cudaSetDevice(h->device));
+    void* scr;
+    int rc = get_scratch(h, gaps_work_bytes(batch, n_samples), &scr);
+    if (rc) return rc;
+    CU(h, launch_gap_span(x, n_samples, batch, n_samples, threshold, 0, scr, (long long*)span, nullptr, (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+int ainmf_find_gaps(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, int32_t min_len,
+                    int64_t* runs, int32_t max_runs, int32_t* n_runs, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || !runs || !n_runs || batch <= 0 || n_samples < 1 || max_runs < 1 || min_len < 0)
+        return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_find_gaps");
+    CU(h, cudaSetDevice(h->device));
+    void* scr;
+    int rc = get_scratch(h, gaps_work_bytes(batch, n_samples), &scr);
+    if (rc) return rc;
+    CU(h, launch_gap_runs(x, n_samples, batch, n_samples, threshold, min_len, scr, (long long*)runs, max_runs, n_runs,
+                          (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+int ainmf_linear_interp(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, float* y,
+                        int64_t* n_damaged, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || !y || batch <= 0 || n_samples < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_linear_interp");
+    CU(h, cudaSetDevice(h->device));
+    void* scr;
+    int rc = get_scratch(h, gaps_work_bytes(batch, n_samples), &scr);
+    if (rc) return rc;
+    CU(h, launch_interp_fill(x, n_samples, batch, n_samples, threshold, scr, y, n_samples, (long long*)n_damaged, (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+int ainmf_blend_boundaries(ainmf_handle h, const float* raw, const float* restored, int64_t n_samples, int64_t gap_start,
+                           int64_t gap_end, int32_t blend_len, float* out, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!raw || !restored || !out || n_samples < 1 || blend_len < 2 || gap_start < blend_len || gap_end < gap_start ||
+        gap_end + blend_len > n_samples)
+        return fail(h, AINMF_ERR_INVALID, "ainmf_blend_boundaries needs blend_len >= 2 and blend_len <= gap_start <= gap_end <= n_samples - blend_len");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, launch_blend(raw, restored, n_samples, gap_start, gap_end, blend_len, out, (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
+int ainmf_snr_db(ainmf_handle h, const float* ref, const float* est, int64_t begin, int64_t end, double* snr_db, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!ref || !est || !snr_db || begin < 0 || end < begin) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_snr_db");
+    CU(h, cudaSetDevice(h->device));
+    void* scr;
+    int rc = get_scratch(h, sizeof(double) * 512, &scr);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, launch_snr_sums(ref, est, begin, end, (double*)scr, s));
+    double part[512];
+    CU(h, cudaMemcpyAsync(part, scr, sizeof part, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    double num = 0.0, den = 0.0;
+    for (int i = 0; i < 256; ++i) { num += part[2 * i]; den += part[2 * i + 1]; }
+    *snr_db = 10.0 * log10(num / (den + 1e-10));
+    return AINMF_OK;
+}
+
 }  // extern "C"
 
 #include "sharded.inc"

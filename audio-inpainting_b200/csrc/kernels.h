@@ -60,6 +60,18 @@ cudaError_t launch_transpose_f32(const float* src, long long src_stride, int ld_
 cudaError_t launch_transpose_c64(const float2* src, long long src_stride, int ld_src, int rows, int cols, float2* dst,
                                  long long dst_stride, int ld_dst, int zero_pad, int B, cudaStream_t s);
 
+// ---- gaps.cu: sample-level detectors / baselines of the sibling scripts and the Part-0 post-processing ----------
+size_t gaps_work_bytes(int B, long long N);
+cudaError_t launch_gap_span(const float* x, long long x_stride, int B, long long N, float thr, int inclusive, void* work,
+                            long long* span, long long* n_gap, cudaStream_t s);
+cudaError_t launch_gap_runs(const float* x, long long x_stride, int B, long long N, float thr, int min_len, void* work,
+                            long long* runs, int max_runs, int* n_runs, cudaStream_t s);
+cudaError_t launch_interp_fill(const float* x, long long x_stride, int B, long long N, float thr, void* work, float* y,
+                               long long y_stride, long long* n_damaged, cudaStream_t s);
+cudaError_t launch_blend(const float* raw, const float* restored, long long N, long long gs, long long ge, int blend_len,
+                         float* out, cudaStream_t s);
+cudaError_t launch_snr_sums(const float* ref, const float* est, long long begin, long long end, double* sums, cudaStream_t s);
+
 // ---- per-clip control block (device) ---------------------------------------------------------------
 struct ClipState {
     int done;            // 1 once the stop rule fired (or nothing to do); kernels of the iteration skip the clip

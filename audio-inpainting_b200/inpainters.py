@@ -202,28 +202,18 @@ class SpectralInpainter:
                                                   self.tol, self.seed, 1e-4, 9, 10, cs, ce, n_iter, None, None)
         self.n_iter_ = int(nit[0])
         self.reconstruction_err_ = float(err[0])
-        self.restored_audio = y[0].cpu().numpy()[:len(self.raw_audio)]
-        self._blend_boundaries()
-        numerator = np.sum(self.raw_audio ** 2)
-        denominator = np.sum((self.raw_audio - self.restored_audio) ** 2)
-        self.snr_ = 10 * np.log10(numerator / (denominator + 1e-10))
-        go = self.raw_audio[self.gap_start:self.gap_end]
-        gr = self.restored_audio[self.gap_start:self.gap_end]
-        self.local_snr_ = 10 * np.log10(np.sum(go ** 2) / (np.sum((go - gr) ** 2) + 1e-10))
+        raw = torch.from_numpy(np.ascontiguousarray(self.raw_audio, np.float32)).to(self.device)
+        final = self._blend_boundaries(raw, y[0][:len(self.raw_audio)].contiguous())
+        self.snr_ = ops.snr_db(raw, final)                                          # main4_NMF.py:99-102
+        self.local_snr_ = ops.snr_db(raw, final, self.gap_start, self.gap_end)      # :104-108
+        self.restored_audio = final.cpu().numpy()
         if self.verbose:
             print(f"SNR: {self.snr_:.2f} dB, Local SNR: {self.local_snr_:.2f} dB")
         return self.restored_audio
 
-    # main4_NMF.py:114-126
-    def _blend_boundaries(self):
-        final = self.raw_audio.copy()
-        gs, ge = self.gap_start, self.gap_end
-        blend_width = 50
-        mask = np.linspace(0, 1, blend_width)
-        final[gs:ge] = self.restored_audio[gs:ge]
-        final[gs - blend_width:gs] = final[gs - blend_width:gs] * (1 - mask) + self.restored_audio[gs - blend_width:gs] * mask
-        final[ge:ge + blend_width] = final[ge:ge + blend_width] * mask + self.restored_audio[ge:ge + blend_width] * (1 - mask)
-        self.restored_audio = final
+    # main4_NMF.py:114-126 (on the device: ops.blend_boundaries reproduces numpy's float64 ramp arithmetic exactly)
+    def _blend_boundaries(self, raw, restored):
+        return ops.blend_boundaries(raw, restored, int(self.gap_start), int(self.gap_end), 50)
 
     # main4_NMF.py:128-137 (WAV part)
     def save_results(self):

@@ -26,6 +26,10 @@ _LIBRARY.define("nmf_inpaint(Tensor x, int n_fft, int hop, int rank, int max_ite
                 "Tensor? W0, Tensor? H0, str solver='cd') -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
 _LIBRARY.define("load_pcm16(Tensor pcm) -> (Tensor, Tensor)")
 _LIBRARY.define("store_pcm16(Tensor y) -> Tensor")
+_LIBRARY.define("find_main_gap(Tensor x, float threshold) -> Tensor")
+_LIBRARY.define("find_gaps(Tensor x, float threshold, int min_len, int max_runs) -> (Tensor, Tensor)")
+_LIBRARY.define("linear_interp(Tensor x, float threshold) -> (Tensor, Tensor)")
+_LIBRARY.define("blend_boundaries(Tensor raw, Tensor restored, int gap_start, int gap_end, int blend_len) -> Tensor")
 
 
 def _dev(t: torch.Tensor) -> int:
@@ -197,6 +201,82 @@ def _store_pcm16(y):
     return out
 
 
+def _find_main_gap(x, threshold):
+    """main3_AR_text_gap.py:34-49 -> [B, 2] int64 {start, end} ({-1, -1}: no gap)."""
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        span = torch.empty((B, 2), dtype=torch.int64, device=x.device)
+        _lib.check(L.ainmf_find_main_gap(_lib.handle(dev), _p(x), B, N, threshold, _p(span), _stream(dev)), dev)
+    return span
+
+
+def _find_gaps(x, threshold, min_len, max_runs):
+    """main3_AR_text_mask.py:30-52 -> (runs [B, max_runs, 2] int64 (-1 padded), n_runs [B] int32)."""
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        runs = torch.full((B, max_runs, 2), -1, dtype=torch.int64, device=x.device)
+        n = torch.empty((B,), dtype=torch.int32, device=x.device)
+        _lib.check(L.ainmf_find_gaps(_lib.handle(dev), _p(x), B, N, threshold, min_len, _p(runs), max_runs, _p(n), _stream(dev)), dev)
+    return runs, n
+
+
+def _linear_interp(x, threshold):
+    """linear_interp_part1.py:52-75 -> (y [B, N], n_damaged [B] int64)."""
+    x = _f32(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("x must be [B, N]")
+    dev = _dev(x)
+    B, N = x.shape
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        y = torch.empty_like(x)
+        nd = torch.empty((B,), dtype=torch.int64, device=x.device)
+        _lib.check(L.ainmf_linear_interp(_lib.handle(dev), _p(x), B, N, threshold, _p(y), _p(nd), _stream(dev)), dev)
+    return y, nd
+
+
+def _blend_boundaries(raw, restored, gap_start, gap_end, blend_len):
+    """main4_NMF.py:114-126 on 1-D signals."""
+    raw, restored = _f32(raw, "raw"), _f32(restored, "restored")
+    if raw.dim() != 1 or raw.shape != restored.shape:
+        raise RuntimeError("raw and restored must be 1-D and of equal length")
+    dev = _dev(raw)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = torch.empty_like(raw)
+        _lib.check(L.ainmf_blend_boundaries(_lib.handle(dev), _p(raw), _p(restored), raw.numel(), gap_start, gap_end, blend_len,
+                                            _p(out), _stream(dev)), dev)
+    return out
+
+
+def snr_db(ref, est, begin=0, end=None):
+    """10 log10(sum ref^2 / (sum (ref - est)^2 + 1e-10)) over [begin, end) (main4_NMF.py:99-110); returns a Python float."""
+    ref, est = _f32(ref, "ref"), _f32(est, "est")
+    if ref.dim() != 1 or ref.shape != est.shape:
+        raise RuntimeError("ref and est must be 1-D and of equal length")
+    dev = _dev(ref)
+    end = ref.numel() if end is None else end
+    out = C.c_double()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.ainmf_snr_db(_lib.handle(dev), _p(ref), _p(est), begin, end, C.byref(out), _stream(dev)), dev)
+    return out.value
+
+
+for _name, _fn in (("find_main_gap", _find_main_gap), ("find_gaps", _find_gaps), ("linear_interp", _linear_interp),
+                   ("blend_boundaries", _blend_boundaries)):
+    _LIBRARY.impl(_name, _fn, "CUDA")
+
 for _name, _fn in (("stft", _stft), ("gap_mask", _gap_mask), ("nmf_fit", _nmf_fit), ("istft", _istft),
                    ("nmf_inpaint", _nmf_inpaint), ("load_pcm16", _load_pcm16), ("store_pcm16", _store_pcm16)):
     _LIBRARY.impl(_name, _fn, "CUDA")
@@ -208,3 +288,7 @@ istft = torch.ops.ainmf.istft
 nmf_inpaint = torch.ops.ainmf.nmf_inpaint
 load_pcm16 = torch.ops.ainmf.load_pcm16
 store_pcm16 = torch.ops.ainmf.store_pcm16
+find_main_gap = torch.ops.ainmf.find_main_gap
+find_gaps = torch.ops.ainmf.find_gaps
+linear_interp = torch.ops.ainmf.linear_interp
+blend_boundaries = torch.ops.ainmf.blend_boundaries

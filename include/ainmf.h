@@ -130,6 +130,27 @@ int ainmf_load_pcm16(ainmf_handle h, const int16_t* pcm, int32_t batch, int64_t 
 /* save_result (main4_NMF_gap.py:76-77): clip to [-1,1], * 32767, truncate toward zero. */
 int ainmf_store_pcm16(ainmf_handle h, const float* y, int64_t count, int16_t* pcm, void* stream);
 
+/* ---- callers / baselines either side of the NMF path ----------------------------------- */
+/* find_main_gap (main3_AR_text_gap.py:34-49): span [B][2] int64 = {first, last + 1} of the samples with
+ * |x| < threshold, {-1, -1} when there is none. */
+int ainmf_find_main_gap(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, int64_t* span,
+                        void* stream);
+/* find_gaps (main3_AR_text_mask.py:30-52): maximal runs [s, e) of |x| < threshold with e - s > min_len (100 in the
+ * script), ascending; runs [B][max_runs][2] int64, n_runs [B] (the count found, which may exceed max_runs). */
+int ainmf_find_gaps(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, int32_t min_len,
+                    int64_t* runs, int32_t max_runs, int32_t* n_runs, void* stream);
+/* linear_interp_part1.py:52-75: valid = |x| > threshold; y = x on valid samples and np.interp over the valid ones
+ * elsewhere (float64 arithmetic, end values outside the valid range).  n_damaged [B] int64 optional. */
+int ainmf_linear_interp(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, float* y,
+                        int64_t* n_damaged, void* stream);
+/* _blend_boundaries (main4_NMF.py:114-126): ground truth outside [gap_start, gap_end), restored inside, linear
+ * cross-fades of blend_len (50) samples either side (np.linspace ramp, float64 arithmetic). */
+int ainmf_blend_boundaries(ainmf_handle h, const float* raw, const float* restored, int64_t n_samples, int64_t gap_start,
+                           int64_t gap_end, int32_t blend_len, float* out, void* stream);
+/* 10 log10(sum ref^2 / (sum (ref - est)^2 + 1e-10)) over samples [begin, end) (main4_NMF.py:99-110); sums in double;
+ * synchronises the stream, result on the host. */
+int ainmf_snr_db(ainmf_handle h, const float* ref, const float* est, int64_t begin, int64_t end, double* snr_db, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------ */
 /* Number of kernels this library has launched in this process (monotonic). */
 unsigned long long ainmf_launch_count(void);

@@ -199,3 +199,38 @@ def centre_gap(n, sr, half_s=1.0):
     centre = n // 2
     half = int(half_s * sr)
     return centre - half, centre + half
+
+
+# ---- sample-level detectors / baselines of the sibling scripts ------------------------------------
+def find_main_gap(x, threshold=1e-4):
+    """main3_AR_text_gap.py:34-49: (start, end) of the samples with |x| < threshold, or None."""
+    idx = np.where(np.abs(x) < threshold)[0]
+    if len(idx) == 0:
+        return None
+    return int(idx[0]), int(idx[-1] + 1)
+
+
+def find_gaps(x, threshold=0.01, min_len=100):
+    """main3_AR_text_mask.py:30-52: runs of |x| < threshold longer than min_len samples."""
+    is_gap = (np.abs(x) < threshold)
+    diff = np.diff(is_gap.astype(int))
+    starts = np.where(diff == 1)[0] + 1
+    ends = np.where(diff == -1)[0] + 1
+    if is_gap[0]:
+        starts = np.insert(starts, 0, 0)
+    if is_gap[-1]:
+        ends = np.append(ends, len(x))
+    return [(int(s), int(e)) for s, e in zip(starts, ends) if (e - s) > min_len]
+
+
+def linear_interp(x, threshold=1e-4):
+    """linear_interp_part1.py:52-75: damaged = not(|x| > threshold) samples <- np.interp over the valid ones.
+    Returns (y float32, number of damaged samples)."""
+    mask = np.abs(x) > threshold
+    n_damaged = int(np.sum(~mask))
+    if n_damaged == 0 or n_damaged == len(x):
+        return x.copy(), n_damaged
+    x_all = np.arange(len(x))
+    y = x.copy()
+    y[~mask] = np.interp(x_all[~mask], x_all[mask], x[mask])
+    return y, n_damaged

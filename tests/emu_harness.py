@@ -129,3 +129,41 @@ def inpaint(x, **kw):
     check(lib().ainmf_inpaint(handle(), C.byref(p), ptr(x), None, None, ptr(y), ptr(idx), ptr(nb), ptr(W), ptr(H),
                               ptr(err), ptr(nit), C.c_void_p(ws.ctypes.data + off), ws_bytes, None))
     return dict(y=y, bad_idx=idx, n_bad=nb, W=W, H=H, err=err, n_iter=nit)
+
+
+# ---- callers / baselines either side of the NMF path (gaps.cu) -------------------------------------------------
+def find_main_gap(x, thr):
+    x = np.ascontiguousarray(x, np.float32)
+    span = np.zeros((x.shape[0], 2), np.int64)
+    check(lib().ainmf_find_main_gap(handle(), ptr(x), x.shape[0], x.shape[1], thr, ptr(span), None))
+    return span
+
+
+def find_gaps(x, thr, min_len, max_runs):
+    x = np.ascontiguousarray(x, np.float32)
+    runs = np.full((x.shape[0], max_runs, 2), -1, np.int64)
+    n = np.zeros(x.shape[0], np.int32)
+    check(lib().ainmf_find_gaps(handle(), ptr(x), x.shape[0], x.shape[1], thr, min_len, ptr(runs), max_runs, ptr(n), None))
+    return runs, n
+
+
+def linear_interp(x, thr):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.zeros_like(x)
+    nd = np.zeros(x.shape[0], np.int64)
+    check(lib().ainmf_linear_interp(handle(), ptr(x), x.shape[0], x.shape[1], thr, ptr(y), ptr(nd), None))
+    return y, nd
+
+
+def blend_boundaries(raw, restored, gs, ge, blend_len):
+    raw = np.ascontiguousarray(raw, np.float32); restored = np.ascontiguousarray(restored, np.float32)
+    out = np.zeros_like(raw)
+    check(lib().ainmf_blend_boundaries(handle(), ptr(raw), ptr(restored), raw.size, gs, ge, blend_len, ptr(out), None))
+    return out
+
+
+def snr_db(ref, est, begin, end):
+    ref = np.ascontiguousarray(ref, np.float32); est = np.ascontiguousarray(est, np.float32)
+    out = C.c_double()
+    check(lib().ainmf_snr_db(handle(), ptr(ref), ptr(est), begin, end, C.byref(out), None))
+    return out.value

@@ -145,3 +145,49 @@ def test_emu_mu_solver_matches_sklearn_mu(F, T, K, iters, tol):
     assert nit[0] == no
     assert abs(err[0] - eo) < 1e-4 * eo
     assert rel_l2(W[0], Wo) < 1e-3 and rel_l2(H[0], Ho) < 1e-3
+
+
+# ---- callers / baselines either side of the NMF path ---------------------------------------
+def _gap_signals():
+    rng = np.random.default_rng(7)
+    out = []
+    for N, kind in ((5000, "gaps"), (9000, "edges"), (3000, "none"), (2049, "all")):
+        x = (rng.standard_normal(N) * 0.3).astype(np.float32)
+        if kind == "gaps":
+            for _ in range(12):
+                s = int(rng.integers(0, N - 500)); l = int(rng.integers(1, 450))
+                x[s:s + l] = 0
+            x[rng.integers(0, N, 50)] = 5e-5
+        elif kind == "edges":
+            x[:300] = 0; x[-1234:] = 0; x[3000:3101] = 0; x[3500:3600] = 0; x[4096:6144] = 0
+        elif kind == "all":
+            x[:] = 0
+        out.append(x)
+    return out
+
+
+@pytest.mark.parametrize("thr", [1e-4, 0.01])
+def test_emu_gap_detectors_bit_exact(thr):
+    for x in _gap_signals():
+        span = E.find_main_gap(x[None], thr)[0]
+        ref = libcalls.find_main_gap(x, thr)
+        assert tuple(span) == (ref if ref is not None else (-1, -1))
+        runs, n = E.find_gaps(x[None], thr, 100, 64)
+        ref_runs = libcalls.find_gaps(x, thr, 100)
+        assert int(n[0]) == len(ref_runs)
+        assert [tuple(r) for r in runs[0, :len(ref_runs)]] == ref_runs
+
+
+def test_emu_linear_interp_blend_snr():
+    for x in _gap_signals():
+        y, nd = E.linear_interp(x[None], 1e-4)
+        yo, no = libcalls.linear_interp(x, 1e-4)
+        assert int(nd[0]) == no
+        assert np.max(np.abs(y[0].astype(np.float64) - yo.astype(np.float64))) <= 1.2e-7 * max(1.0, float(np.max(np.abs(yo))))
+    rng = np.random.default_rng(3)
+    raw = (rng.standard_normal(2205) * 0.4).astype(np.float32)
+    res = (raw + 0.05 * rng.standard_normal(2205)).astype(np.float32)
+    out = E.blend_boundaries(raw, res, 882, 1323, 50)
+    ref = libcalls.part0_blend(raw, res, 882, 1323)
+    assert np.array_equal(out, ref)
+    assert abs(E.snr_db(raw, out, 882, 1323) - libcalls.snr_db(raw[882:1323], ref[882:1323])) < 1e-3
