@@ -474,9 +474,18 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                     for (int j = 0; j < TJ; ++j) fj[j] = row[c0 + j];
                 }
 #pragma unroll
-                for (int i = 0; i < TI; ++i)
+                for (int i = 0; i < TI; ++i) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
+#pragma unroll
+                    for (int j = 0; j < TJ; j += 2) {
+                        const float2 r2 = __ffma2_rn(make_float2(fi[i], fi[i]), make_float2(fj[j], fj[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+                        acc[i][j] = r2.x; acc[i][j + 1] = r2.y;
+                    }
+#else
 #pragma unroll
                     for (int j = 0; j < TJ; ++j) acc[i][j] = fmaf(fi[i], fj[j], acc[i][j]);
+#endif
+                }
             }
 #pragma unroll
             for (int i = 0; i < TI; ++i)

@@ -181,10 +181,23 @@ def cpu_leg(wl, n_clips, first_clip=0):
     return dt, its, outs
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use every host core (OpenBLAS inside
+    sklearn / numpy), so lift the limit at run time.  Returns the thread count in effect."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=cores)
+        n = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        return n
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", cores))
+
+
 def run_reference(args, wl, rank):
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = use_all_host_threads()
     clips_per_step = 2 if wl["clips"] > 1 else 1
     for _ in range(args.warmup):
         cpu_leg(wl, 1)
@@ -538,8 +551,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import libcalls
         n_cpu = 8 if B > 1 else 1
+        cores = use_all_host_threads()
         dt, its, outs = cpu_leg(wl, n_cpu)
-        cores = os.cpu_count()
         cpu = {"value": n_cpu * N / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} clips of the workload, serially, through scipy.signal.stft/istft + sklearn NMF(cd) "
                          f"(oracle/libcalls.py); OpenBLAS threads = {cores}, coordinate sweep single-threaded",
