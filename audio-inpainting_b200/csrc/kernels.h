@@ -147,10 +147,10 @@ struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXs, mapHs, mapHmn, mapHk, map
 
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64, w_lanes = 1, w_rows = 128;
-    // tensor-core path (tcgen05, error-compensated TF32) for the two V-sized contractions; KP in {64,128}
+    // tensor-core path (tcgen05: tf32 main term + bf16 cross terms) for the two V-sized contractions; KP in {64,128}
     int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
-    float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed, and its TF32 residual
-    float* tc_GLo = nullptr;                      // [B][KP][KP]: TF32 residual of W^T W
+    float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed (tf32 main-term operand), and its bf16 cross-term operand (tc::cross_pack8)
+    float* tc_GLo = nullptr;                      // [B][KP][KP]: bf16 cross-term operand of W^T W
     float* tc_blobs = nullptr;                    // [B][KP/8][16*KP]: per-block update operands of the sweep (nmf_ts.cu: g_prep_kernel)
     float* tc_scal = nullptr;                     // [B][KP/8][136]: per-block sweep scalars
     const TcMaps* tc = nullptr;

@@ -155,8 +155,9 @@ int ainmf_snr_db(ainmf_handle h, const float* ref, const float* est, int64_t beg
 /* Number of kernels this library has launched in this process (monotonic). */
 unsigned long long ainmf_launch_count(void);
 /* Kernel timing of the NMF iteration with CUDA events on the launching stream.  Reads (and clears) the time
- * accumulated since the last call into ms_out[6] / counts_out[6] -- order: gram(Ht), X.Ht partials, W sweep,
- * gram(W), fused X^T.W + H sweep, stop rule -- then switches recording on or off.  ms_out/counts_out may be NULL. */
+ * accumulated since the last call into ms_out[6] / counts_out[6] -- order: gram(Ht) [FFMA path only], X.Ht partials
+ * (+ Gram of Ht on the tensor-core path), W side (sweep, W^T W, operands of the H step), gram(W) [MU solver only],
+ * fused X^T.W + H sweep, stop rule -- then switches recording on or off.  ms_out/counts_out may be NULL. */
 int ainmf_profile(ainmf_handle h, int32_t enable, double* ms_out, int64_t* counts_out);
 
 /* ---- time-frame sharding of one long signal ------------------------------------------------- */
