@@ -13,7 +13,7 @@ EXPORTS = [
     "ainmf_workspace_bytes", "ainmf_inpaint", "ainmf_inpaint_host", "ainmf_load_pcm16", "ainmf_store_pcm16",
     "ainmf_comm_unique_id", "ainmf_comm_init", "ainmf_shard_plan", "ainmf_sharded_workspace_bytes",
     "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile", "ainmf_comm_set_callbacks",
-    "ainmf_find_main_gap", "ainmf_find_gaps", "ainmf_linear_interp", "ainmf_blend_boundaries", "ainmf_snr_db",
+    "ainmf_find_main_gap", "ainmf_find_gaps", "ainmf_linear_interp", "ainmf_blend_boundaries", "ainmf_snr_db", "ainmf_apply_gaps",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
@@ -53,6 +53,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "ainmf_find_main_gap": (C.c_int, [vp, vp, i32, i64, f32, vp, vp]),
         "ainmf_find_gaps": (C.c_int, [vp, vp, i32, i64, f32, i32, vp, i32, vp, vp]),
         "ainmf_linear_interp": (C.c_int, [vp, vp, i32, i64, f32, vp, vp, vp]),
+        "ainmf_apply_gaps": (C.c_int, [vp, vp, i32, i64, vp, vp, i32, vp]),
         "ainmf_blend_boundaries": (C.c_int, [vp, vp, vp, i64, i64, i64, i32, vp, vp]),
         "ainmf_snr_db": (C.c_int, [vp, vp, vp, i64, i64, P(C.c_double), vp]),
         "ainmf_launch_count": (C.c_ulonglong, []),

@@ -764,6 +764,17 @@ int ainmf_linear_interp(ainmf_handle h, const float* x, int32_t batch, int64_t n
     return AINMF_OK;
 }
 
+int ainmf_apply_gaps(ainmf_handle h, float* x, int32_t batch, int64_t n_samples, const int64_t* starts, const int64_t* lens,
+                     int32_t gaps_per_clip, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!x || !starts || !lens || batch <= 0 || n_samples < 1 || gaps_per_clip < 1)
+        return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_apply_gaps");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, launch_apply_gaps(x, n_samples, batch, n_samples, (const long long*)starts, (const long long*)lens, gaps_per_clip,
+                            (cudaStream_t)stream));
+    return AINMF_OK;
+}
+
 int ainmf_blend_boundaries(ainmf_handle h, const float* raw, const float* restored, int64_t n_samples, int64_t gap_start,
                            int64_t gap_end, int32_t blend_len, float* out, void* stream) {
     if (!h) return AINMF_ERR_INVALID;

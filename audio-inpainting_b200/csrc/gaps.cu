@@ -273,6 +273,19 @@ snr_sums_kernel(const float* __restrict__ ref, const float* __restrict__ est, lo
     }
 }
 
+// Fixture producers: x[b][s : s + l] = 0 for the clip's gap list -- the zeroing loop of
+// generate_part1_data.py:44-46 (gaps from create_random_mask, drawn on the host) and generate_part2_data.py:36-43.
+// grid = (gaps per clip, B); a gap may extend past N (clipped) and gaps may overlap.
+__global__ void __launch_bounds__(kThreads)
+apply_gaps_kernel(float* __restrict__ x, long long x_stride, long long N, const long long* __restrict__ starts,
+                  const long long* __restrict__ lens, int gaps_per_clip) {
+    const int b = blockIdx.y, g = blockIdx.x;
+    const long long s = starts[(long long)b * gaps_per_clip + g], l = lens[(long long)b * gaps_per_clip + g];
+    if (s < 0 || l <= 0) return;
+    const long long e = (s + l < N) ? s + l : N;
+    for (long long i = s + threadIdx.x; i < e; i += blockDim.x) x[(long long)b * x_stride + i] = 0.f;
+}
+
 // ---- launchers --------------------------------------------------------------------------------------------------
 size_t gaps_work_bytes(int B, long long N) {
     const long long chunks = (N + GC - 1) / GC;
@@ -337,6 +350,12 @@ cudaError_t launch_interp_fill(const float* x, long long x_stride, int B, long l
     if (n_damaged) e = cudaMemcpy2DAsync(n_damaged, sizeof(long long), w.totals + 2, 4 * sizeof(long long), sizeof(long long), B,
                                          cudaMemcpyDeviceToDevice, s);
     return e;
+}
+
+cudaError_t launch_apply_gaps(float* x, long long x_stride, int B, long long N, const long long* starts, const long long* lens,
+                              int gaps_per_clip, cudaStream_t s) {
+    AINMF_LAUNCH(apply_gaps_kernel, dim3(gaps_per_clip, B), dim3(kThreads), 0, s, x, x_stride, N, starts, lens, gaps_per_clip);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_blend(const float* raw, const float* restored, long long N, long long gs, long long ge, int blend_len,

@@ -68,6 +68,8 @@ cudaError_t launch_gap_runs(const float* x, long long x_stride, int B, long long
                             long long* runs, int max_runs, int* n_runs, cudaStream_t s);
 cudaError_t launch_interp_fill(const float* x, long long x_stride, int B, long long N, float thr, void* work, float* y,
                                long long y_stride, long long* n_damaged, cudaStream_t s);
+cudaError_t launch_apply_gaps(float* x, long long x_stride, int B, long long N, const long long* starts, const long long* lens,
+                              int gaps_per_clip, cudaStream_t s);
 cudaError_t launch_blend(const float* raw, const float* restored, long long N, long long gs, long long ge, int blend_len,
                          float* out, cudaStream_t s);
 cudaError_t launch_snr_sums(const float* ref, const float* est, long long begin, long long end, double* sums, cudaStream_t s);

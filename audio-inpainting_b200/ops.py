@@ -259,6 +259,23 @@ def _blend_boundaries(raw, restored, gap_start, gap_end, blend_len):
     return out
 
 
+def apply_gaps_(x, starts, lens):
+    """In place: x[b, s:s+l] = 0 for the gap lists starts/lens [B, G] (int64, device) -- the zeroing step of the fixture
+    producers (generate_part1_data.py:44-46, generate_part2_data.py:36-43)."""
+    x = _f32(x, "x")
+    if x.dim() != 2 or starts.shape != lens.shape or starts.dim() != 2 or starts.shape[0] != x.shape[0]:
+        raise RuntimeError("x must be [B, N] and starts/lens [B, G]")
+    if starts.dtype != torch.int64 or lens.dtype != torch.int64:
+        raise RuntimeError("starts and lens must be int64")
+    dev = _dev(x)
+    starts, lens = starts.contiguous(), lens.contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.ainmf_apply_gaps(_lib.handle(dev), _p(x), x.shape[0], x.shape[1], _p(starts), _p(lens), starts.shape[1],
+                                      _stream(dev)), dev)
+    return x
+
+
 def snr_db(ref, est, begin=0, end=None):
     """10 log10(sum ref^2 / (sum (ref - est)^2 + 1e-10)) over [begin, end) (main4_NMF.py:99-110); returns a Python float."""
     ref, est = _f32(ref, "ref"), _f32(est, "est")

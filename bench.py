@@ -98,15 +98,11 @@ def synth_device(wl, b0, B, device):
     x += 0.02 * torch.randn((B, N), device=device, generator=g)
     x /= x.abs().amax(dim=1, keepdim=True)
     if wl["thr"] > 1e-3:
-        diff = torch.zeros((B, N + 1), device=device, dtype=torch.int32)
-        for i in range(B):
-            s, l = mask_gaps(N, b0 + i)
-            sd = torch.from_numpy(s).to(device)
-            ed = torch.from_numpy(s + l).to(device)
-            diff[i].index_add_(0, sd, torch.ones_like(sd, dtype=torch.int32))
-            diff[i].index_add_(0, ed, -torch.ones_like(ed, dtype=torch.int32))
-        x[diff.cumsum(1)[:, :N] > 0] = 0
-        del diff
+        import ainmf
+        gl = [mask_gaps(N, b0 + i) for i in range(B)]
+        starts = torch.from_numpy(np.stack([g[0] for g in gl])).to(device)
+        lens = torch.from_numpy(np.stack([g[1] for g in gl])).to(device)
+        ainmf.ops.apply_gaps_(x, starts, lens)              # the zeroing loop of generate_part1_data.py:44-46 on the device
     else:
         c = N // 2
         x[:, c - SR:c + SR] = 0

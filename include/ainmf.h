@@ -143,6 +143,11 @@ int ainmf_find_gaps(ainmf_handle h, const float* x, int32_t batch, int64_t n_sam
  * elsewhere (float64 arithmetic, end values outside the valid range).  n_damaged [B] int64 optional. */
 int ainmf_linear_interp(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, float threshold, float* y,
                         int64_t* n_damaged, void* stream);
+/* Fixture producers (generate_part1_data.py:44-46 after create_random_mask, generate_part2_data.py:36-43): zero
+ * x[b][s : s + l) for the clip's gaps_per_clip gaps; starts/lens [B][gaps_per_clip] int64 on the device (drawn by the
+ * caller, e.g. with np.random.seed(clip)); entries with a negative start or non-positive length are skipped. */
+int ainmf_apply_gaps(ainmf_handle h, float* x, int32_t batch, int64_t n_samples, const int64_t* starts, const int64_t* lens,
+                     int32_t gaps_per_clip, void* stream);
 /* _blend_boundaries (main4_NMF.py:114-126): ground truth outside [gap_start, gap_end), restored inside, linear
  * cross-fades of blend_len (50) samples either side (np.linspace ramp, float64 arithmetic). */
 int ainmf_blend_boundaries(ainmf_handle h, const float* raw, const float* restored, int64_t n_samples, int64_t gap_start,

@@ -167,3 +167,10 @@ def snr_db(ref, est, begin, end):
     out = C.c_double()
     check(lib().ainmf_snr_db(handle(), ptr(ref), ptr(est), begin, end, C.byref(out), None))
     return out.value
+
+
+def apply_gaps(x, starts, lens):
+    x = np.ascontiguousarray(x, np.float32).copy()
+    starts = np.ascontiguousarray(starts, np.int64); lens = np.ascontiguousarray(lens, np.int64)
+    check(lib().ainmf_apply_gaps(handle(), ptr(x), x.shape[0], x.shape[1], ptr(starts), ptr(lens), starts.shape[1], None))
+    return x

@@ -191,3 +191,26 @@ def test_emu_linear_interp_blend_snr():
     ref = libcalls.part0_blend(raw, res, 882, 1323)
     assert np.array_equal(out, ref)
     assert abs(E.snr_db(raw, out, 882, 1323) - libcalls.snr_db(raw[882:1323], ref[882:1323])) < 1e-3
+
+
+def test_emu_apply_gaps_matches_generate_part1():
+    """create_random_mask semantics (generate_part1_data.py:26-35, 44-46): gap list drawn on the host, zeroed on the device."""
+    rng = np.random.default_rng(5)
+    N = 20000
+    x = (rng.standard_normal((3, N)) * 0.3 + 1.0).astype(np.float32)
+    starts = np.empty((3, 40), np.int64); lens = np.empty((3, 40), np.int64)
+    for b in range(3):
+        np.random.seed(b)
+        for g in range(40):
+            l = np.random.randint(50, 400); s = np.random.randint(0, N - l)
+            starts[b, g], lens[b, g] = s, l
+    starts[2, 5], lens[2, 5] = N - 10, 400          # clipped at N
+    lens[1, 7] = 0                                  # skipped entry
+    starts[0, 3] = -1                               # skipped entry
+    ref = x.copy()
+    for b in range(3):
+        for g in range(40):
+            if starts[b, g] >= 0 and lens[b, g] > 0:
+                ref[b, starts[b, g]:min(N, starts[b, g] + lens[b, g])] = 0
+    out = E.apply_gaps(x, starts, lens)
+    assert np.array_equal(out, ref)

@@ -82,3 +82,20 @@ def test_blend_and_snr_match_part0(golden):
     for (b, e) in ((0, 2205), (gs, ge)):
         s = ainmf.ops.snr_db(dev(raw), dev(out), b, e)
         assert abs(s - libcalls.snr_db(raw[b:e], ref[b:e])) < 1e-3
+
+
+def test_apply_gaps_matches_generate_part1():
+    import ainmf
+    rng = np.random.default_rng(5)
+    N = 441000
+    x = (rng.standard_normal((2, N)) * 0.3 + 1.0).astype(np.float32)
+    starts = np.empty((2, 551), np.int64); lens = np.empty((2, 551), np.int64)
+    ref = x.copy()
+    for b in range(2):
+        np.random.seed(b)
+        for g in range(551):                        # generate_part1_data.create_random_mask(N, 0.25, 400)
+            l = np.random.randint(50, 400); s = np.random.randint(0, N - l)
+            ref[b, s:s + l] = 0
+            starts[b, g], lens[b, g] = s, l
+    out = ainmf.ops.apply_gaps_(dev(x), dev(starts), dev(lens)).cpu().numpy()
+    assert np.array_equal(out, ref)
