@@ -23,6 +23,7 @@ def golden():
         c1 = np.load(os.path.join(GOLDEN, "c1_part0.npz"))
         c2 = np.load(os.path.join(GOLDEN, "c2_gap.npz"))
         c3 = np.load(os.path.join(GOLDEN, "c3_mask.npz"))
+        f4 = np.load(os.path.join(GOLDEN, "f4_siblings.npz"))
         sr = 44100
 
         @staticmethod

@@ -132,3 +132,54 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def siblings():
+    """the sample-level detectors of main3_AR_text_gap.py / main3_AR_text_mask.py (class bodies executed
+    unmodified; the module tails that run the AR restoration are not) and linear_interp_part1.py run as shipped."""
+    import contextlib
+    import io
+
+    def class_namespace(script):
+        src = open(os.path.join(REF, script)).read()
+        head = src[:src.index("\nlab = ")]                   # everything before the module tail
+        ref_loader._stub_matplotlib()
+        ns = {}
+        exec(compile(head, os.path.join(REF, script), "exec"), ns)
+        return ns
+
+    sr, dg = rd("demo_assets/part2/damaged_gap.wav")
+    x_gap = libcalls.load_normalised(dg)
+    _, dr = rd("demo_assets/part1/damaged_random.wav")
+    x_rand = libcalls.load_normalised(dr)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        ns = class_namespace("main3_AR_text_gap.py")
+        a = ns["ARFairGapInpainter"].__new__(ns["ARFairGapInpainter"])
+        a.signal = x_gap
+        span = a.find_main_gap()
+        ns = class_namespace("main3_AR_text_mask.py")
+        m = ns["IterativeARInpainter"].__new__(ns["IterativeARInpainter"])
+        m.signal = x_rand
+        gaps = m.find_gaps()
+        m.signal = x_gap
+        gaps_on_gap = m.find_gaps()
+        with ref_loader.scratch_cwd({"demo_assets/part1/damaged_random.wav": os.path.join(REF, "demo_assets/part1/damaged_random.wav")}):
+            li = ref_loader.load("linear_interp_part1")
+            li.linear_interpolation_restoration()
+            fixed = wavfile.read("demo_assets/part1/fixed_linear_random.wav")[1]
+    assert tuple(span) == libcalls.find_main_gap(x_gap, 1e-4)
+    assert [tuple(g) for g in gaps] == libcalls.find_gaps(x_rand, 0.01, 100)
+    assert [tuple(g) for g in gaps_on_gap] == libcalls.find_gaps(x_gap, 0.01, 100)
+    # linear_interp_part1.py normalises without the mono/zero guards of the loaders: data.astype(float32) / max|data|
+    xr = dr.astype(np.float32) / np.max(np.abs(dr))
+    y, nd = libcalls.linear_interp(xr, 1e-4)
+    assert np.array_equal(libcalls.quantise_int16(y), fixed), "oracle linear_interp differs from linear_interp_part1.py"
+    np.savez_compressed(os.path.join(OUT, "f4_siblings.npz"), main_gap=np.array(span, np.int64),
+                        gaps_random=np.array(gaps, np.int64).reshape(-1, 2), gaps_on_gap=np.array(gaps_on_gap, np.int64).reshape(-1, 2),
+                        damaged_random_i16=dr, fixed_linear_i16=fixed, n_damaged=np.int64(nd))
+    print("F4: main gap", tuple(span), "| find_gaps on damaged_random:", len(gaps), "runs | linear interp:", nd, "damaged samples, int16 output bit-equal")
+
+
+if __name__ == "__main__" and "--siblings" in sys.argv:
+    siblings()

@@ -99,3 +99,20 @@ def test_apply_gaps_matches_generate_part1():
             starts[b, g], lens[b, g] = s, l
     out = ainmf.ops.apply_gaps_(dev(x), dev(starts), dev(lens)).cpu().numpy()
     assert np.array_equal(out, ref)
+
+
+def test_f4_golden_outputs_of_the_reference_scripts(golden):
+    """Device kernels vs what the unmodified sibling scripts produced (tests/golden/f4_siblings.npz)."""
+    import ainmf
+    f4 = golden.f4
+    x_gap = libcalls.load_normalised(golden.gap_input_i16())
+    span = ainmf.ops.find_main_gap(dev(x_gap[None]), 1e-4)[0].cpu().numpy()
+    assert tuple(span) == tuple(f4["main_gap"])
+    dr = f4["damaged_random_i16"]
+    runs, n = ainmf.ops.find_gaps(dev(libcalls.load_normalised(dr)[None]), 0.01, 100, 256)
+    assert int(n[0]) == len(f4["gaps_random"]) and np.array_equal(runs[0, :int(n[0])].cpu().numpy(), f4["gaps_random"])
+    xr = dr.astype(np.float32) / np.max(np.abs(dr))
+    y, nd = ainmf.ops.linear_interp(dev(xr[None]), 1e-4)
+    assert int(nd[0]) == int(f4["n_damaged"])
+    pcm = ainmf.ops.store_pcm16(y[0]).cpu().numpy()
+    assert np.max(np.abs(pcm.astype(np.int32) - f4["fixed_linear_i16"].astype(np.int32))) <= 1      # int16 LSB (1-ulp float ties)

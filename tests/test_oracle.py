@@ -192,3 +192,18 @@ def test_restate_pipeline_matches_libcalls_c2(golden, x_gap):
     assert abs(st["err"] - sl["err"]) < 1e-4 * sl["err"]
     gs, ge = golden.c2["gap"]
     assert libcalls.snr_db(yl, y) > 60 and libcalls.snr_db(yl[gs:ge], y[gs:ge]) > 40
+
+
+def test_f4_sibling_detectors_reproduce_reference_scripts(golden):
+    """oracle restatements vs outputs of the unmodified main3_AR_text_gap.py / main3_AR_text_mask.py class
+    methods and of linear_interp_part1.py run as shipped (tests/golden/make_golden.py --siblings)."""
+    f4 = golden.f4
+    x_gap = libcalls.load_normalised(golden.gap_input_i16())
+    assert libcalls.find_main_gap(x_gap, 1e-4) == tuple(int(v) for v in f4["main_gap"])
+    assert libcalls.find_gaps(x_gap, 0.01, 100) == [tuple(int(v) for v in r) for r in f4["gaps_on_gap"]]
+    dr = f4["damaged_random_i16"]
+    assert libcalls.find_gaps(libcalls.load_normalised(dr), 0.01, 100) == [tuple(int(v) for v in r) for r in f4["gaps_random"]]
+    xr = dr.astype(np.float32) / np.max(np.abs(dr))                      # linear_interp_part1.py:46
+    y, nd = libcalls.linear_interp(xr, 1e-4)
+    assert nd == int(f4["n_damaged"])
+    assert np.array_equal(libcalls.quantise_int16(y), f4["fixed_linear_i16"])
