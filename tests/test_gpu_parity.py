@@ -193,6 +193,25 @@ def test_nmf_fit_batch_is_independent(ops):
         assert float(err[b]) == float(eb[0])
 
 
+def test_tensor_core_path_skips_converged_clips(ops):
+    """Persistent tensor-core kernels walk (clip, tile) lists and skip clips whose stop rule fired: a batch in which one
+    clip converges early must give every clip exactly what it gets alone (K = 64, T >= 128: tcgen05 path)."""
+    rng = np.random.default_rng(21)
+    F, T, K = 257, 300, 64
+    easy = np.abs(rng.standard_normal((F, 3))).astype(np.float32) @ np.abs(rng.standard_normal((3, T))).astype(np.float32)
+    hard = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    X = np.stack([easy, hard, easy * 0.5 + 0.01 * hard]).astype(np.float32)
+    W, H, err, nit = ops.nmf_fit(dev(X), K, 120, 2e-3, 7, None, None)
+    nits = [int(v) for v in nit]
+    assert min(nits) < max(nits), nits                                  # at least one clip stopped before another
+    for b in range(3):
+        Wb, Hb, eb, nb = ops.nmf_fit(dev(X[b:b + 1]), K, 120, 2e-3, 7, None, None)
+        assert int(nb[0]) == nits[b]
+        assert torch.equal(W[b], Wb[0]) and torch.equal(H[b], Hb[0]) and float(err[b]) == float(eb[0])
+    Wo, Ho, no, eo = libcalls.nmf_fit(X[1], K, seed=7, max_iter=120, tol=2e-3)
+    assert abs(nits[1] - no) <= 2 and abs(float(err[1]) - eo) <= 1e-3 * eo
+
+
 def test_nmf_objective_is_monotone(ops):
     rng = np.random.default_rng(9)
     X = np.abs(rng.standard_normal((1, 513, 400))).astype(np.float32)
