@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -240,6 +241,8 @@ struct Plan {
     NmfWork nw;
     size_t off_V = 0, off_Z = 0, off_bad = 0, off_excl = 0, off_idx = 0, off_nbad = 0, off_nexcl = 0, off_fill = 0,
            off_state = 0, off_W = 0, off_Ht = 0, off_imp = 0, off_nmf = 0, off_notdone = 0, total = 0;
+    bool compact = false;           // fit on good-first permuted frames (tensor-core path, n_outer == 1)
+    size_t off_Xp = 0, off_Htp = 0, off_perm = 0, off_gidx = 0, off_gflags = 0, off_tgood = 0;
     long long vz_stride = 0, bad_stride = 0, w_stride = 0, h_stride = 0;
 };
 
@@ -288,6 +291,20 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     pl->off_imp = take(impute_work_bytes(B, F, pl->iw));
     pl->off_nmf = take(nmf_work_bytes(B, T, F, KP, pl->nw));
     pl->off_notdone = take(sizeof(int) * 4);
+    {
+        const char* nc = getenv("AINMF_NO_COMPACT");
+        // worth it once the tiles fill the machine (a single short clip only pays the extra small launches)
+        pl->compact = pl->nw.use_tc && p->n_outer == 1 && p->solver == AINMF_SOLVER_CD && !(nc && nc[0] == '1') &&
+                      (long long)B * ceil_div(T, 128) >= h->n_sm;
+    }
+    if (pl->compact) {
+        pl->off_Xp = take(sizeof(float) * (size_t)B * pl->vz_stride);
+        pl->off_Htp = take(sizeof(float) * (size_t)B * pl->h_stride);
+        pl->off_perm = take(sizeof(int) * (size_t)B * T);
+        pl->off_gidx = take(sizeof(int) * (size_t)B * T);
+        pl->off_gflags = take((size_t)B * pl->bad_stride);
+        pl->off_tgood = take(sizeof(int) * (size_t)B);
+    }
     pl->total = o;
     return 0;
 }
@@ -587,8 +604,18 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     pr.W = (float*)(base + pl.off_W); pr.w_stride = pl.w_stride;
     pr.Ht = (float*)(base + pl.off_Ht); pr.h_stride = pl.h_stride;
     pr.state = st;
+    // the fit itself may run on a good-first permutation of the frames (prf); everything else uses the original order
+    NmfProblem prf = pr;
+    int* perm = nullptr; int* d_tgood = nullptr;
+    if (pl.compact) {
+        prf.Xt = (float*)(base + pl.off_Xp);
+        prf.Ht = (float*)(base + pl.off_Htp);
+        perm = (int*)(base + pl.off_perm);
+        d_tgood = (int*)(base + pl.off_tgood);
+        prf.t_good = d_tgood; prf.fill = fill; prf.fill_stride = ldf;
+    }
     TcMaps tcm;
-    if (nmf_tc_setup(pr, &pl.nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (nmf_tc_setup(prf, &pl.nw, &tcm)) return fail(h, AINMF_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     if (pl.nw.zero_flags) CU(h, cudaMemsetAsync(pl.nw.zero_flags, 0, (size_t)B * pl.nw.zero_stride, s));
 
     CU(h, cudaMemsetAsync(pl.nw.counters, 0, sizeof(unsigned) * B, s));
@@ -627,7 +654,17 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
             if (W0) CU(h, launch_pack_factors(W0, H0, B, F, T, K, KP, pr.W, pr.w_stride, pr.Ht, pr.h_stride, s));
             else CU(h, launch_init_factors(Wn, Hn, T, 0, B, F, T, K, KP, st, pr.W, pr.w_stride, pr.Ht, pr.h_stride, s));
             // a7: the fit
-            if ((rc = run_iterations(h, pr, pl.nw, p->max_iter, p->tol, d_flag, s))) return rc;
+            if (pl.compact) {
+                unsigned char* gflags = (unsigned char*)(base + pl.off_gflags);
+                int* gidx = (int*)(base + pl.off_gidx);
+                CU(h, launch_invert_flags(bad, pl.bad_stride, B, T, gflags, s));
+                CU(h, launch_compact(gflags, pl.bad_stride, B, T, gidx, T, d_tgood, s));
+                CU(h, launch_build_perm(gidx, d_tgood, idx, B, T, perm, s));
+                CU(h, launch_gather_rows(V, pl.vz_stride, prf.Xt, pl.vz_stride, ldf, perm, B, T, d_tgood, s));
+                CU(h, launch_gather_rows(pr.Ht, pr.h_stride, prf.Ht, pr.h_stride, KP, perm, B, T, nullptr, s));
+            }
+            if ((rc = run_iterations(h, prf, pl.nw, p->max_iter, p->tol, d_flag, s))) return rc;
+            if (pl.compact) CU(h, launch_scatter_rows(prf.Ht, pr.h_stride, pr.Ht, pr.h_stride, KP, perm, B, T, s));
             // a8 + a9: objective, then bad frames <- (W H) frames
             CU(h, nmf_finalize(pr, pl.nw, bad, pl.bad_stride, s));
         }

@@ -298,4 +298,69 @@ cudaError_t launch_reset_state(ClipState* st, int B, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- frame permutation for the fit (good frames first) ----------------------------------------------------
+// Every bad frame of the imputed spectrogram is the same column (the fill spectrum), so the tensor-core kernels can skip
+// their share of the two contractions when the frames are ordered good-first.  perm[b][t'] = original frame.
+__global__ void __launch_bounds__(kThreads)
+invert_flags_kernel(const unsigned char* __restrict__ bad, long long stride, int T, unsigned char* __restrict__ good) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) good[(long long)b * stride + t] = bad[(long long)b * stride + t] ? 0 : 1;
+}
+__global__ void __launch_bounds__(kThreads)
+build_perm_kernel(const int* __restrict__ good_idx, const int* __restrict__ n_good, const int* __restrict__ bad_idx, int T,
+                  int* __restrict__ perm) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int ng = n_good[b];
+    perm[(long long)b * T + t] = (t < ng) ? good_idx[(long long)b * T + t] : bad_idx[(long long)b * T + (t - ng)];
+}
+// dst[b][t'][:] = src[b][perm[t']][:] for t' < limit[b] (limit null: all T rows), zeros beyond; one warp per row
+__global__ void __launch_bounds__(kThreads)
+gather_rows_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst, long long dst_stride, int ld,
+                   const int* __restrict__ perm, int T, const int* __restrict__ limit) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= T) return;
+    float4* d = reinterpret_cast<float4*>(dst + (long long)b * dst_stride + (long long)t * ld);
+    if (limit && t >= limit[b]) {
+        for (int i = lane; i < ld / 4; i += 32) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float4* sr = reinterpret_cast<const float4*>(src + (long long)b * src_stride + (long long)perm[(long long)b * T + t] * ld);
+    for (int i = lane; i < ld / 4; i += 32) d[i] = sr[i];
+}
+// dst[b][perm[t']][:] = src[b][t'][:]
+__global__ void __launch_bounds__(kThreads)
+scatter_rows_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst, long long dst_stride, int ld,
+                    const int* __restrict__ perm, int T) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const float4* sr = reinterpret_cast<const float4*>(src + (long long)b * src_stride + (long long)t * ld);
+    float4* d = reinterpret_cast<float4*>(dst + (long long)b * dst_stride + (long long)perm[(long long)b * T + t] * ld);
+    for (int i = lane; i < ld / 4; i += 32) d[i] = sr[i];
+}
+cudaError_t launch_invert_flags(const unsigned char* bad, long long stride, int B, int T, unsigned char* good, cudaStream_t s) {
+    AINMF_LAUNCH(invert_flags_kernel, dim3(ceil_div(T, kThreads), B), dim3(kThreads), 0, s, bad, stride, T, good);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_perm(const int* good_idx, const int* n_good, const int* bad_idx, int B, int T, int* perm, cudaStream_t s) {
+    AINMF_LAUNCH(build_perm_kernel, dim3(ceil_div(T, kThreads), B), dim3(kThreads), 0, s, good_idx, n_good, bad_idx, T, perm);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_rows(const float* src, long long src_stride, float* dst, long long dst_stride, int ld, const int* perm,
+                               int B, int T, const int* limit, cudaStream_t s) {
+    AINMF_LAUNCH(gather_rows_kernel, dim3(ceil_div(T, kThreads / 32), B), dim3(kThreads), 0, s, src, src_stride, dst, dst_stride, ld,
+                 perm, T, limit);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_rows(const float* src, long long src_stride, float* dst, long long dst_stride, int ld, const int* perm,
+                                int B, int T, cudaStream_t s) {
+    AINMF_LAUNCH(scatter_rows_kernel, dim3(ceil_div(T, kThreads / 32), B), dim3(kThreads), 0, s, src, src_stride, dst, dst_stride, ld,
+                 perm, T);
+    return cudaGetLastError();
+}
+
 }  // namespace ainmf

@@ -122,6 +122,13 @@ cudaError_t launch_unpack_factors(const float* W, long long w_stride, const floa
 // copy selected ClipState fields into plain arrays (any may be null)
 cudaError_t launch_export_state(const ClipState* st, int B, int* n_bad, int* n_iter, float* err, int* status,
                                 cudaStream_t s);
+// frame permutation for the fit: good frames first (perm[b][t'] = original frame), row gather / scatter
+cudaError_t launch_invert_flags(const unsigned char* bad, long long stride, int B, int T, unsigned char* good, cudaStream_t s);
+cudaError_t launch_build_perm(const int* good_idx, const int* n_good, const int* bad_idx, int B, int T, int* perm, cudaStream_t s);
+cudaError_t launch_gather_rows(const float* src, long long src_stride, float* dst, long long dst_stride, int ld, const int* perm,
+                               int B, int T, const int* limit, cudaStream_t s);
+cudaError_t launch_scatter_rows(const float* src, long long src_stride, float* dst, long long dst_stride, int ld, const int* perm,
+                                int B, int T, cudaStream_t s);
 // state for a fit on a caller-provided X (no imputation stage): done=0, n_iter=0
 cudaError_t launch_reset_state(ClipState* st, int B, cudaStream_t s);
 
@@ -141,11 +148,16 @@ struct NmfProblem {
     float* Xt; long long x_stride;      // [B][T][ldf]
     float* W; long long w_stride;       // [B][F][KP]
     float* Ht; long long h_stride;      // [B][T][KP]
+    // good-first frame order (tensor-core path, one fit): frames t >= t_good[b] are bad = all equal to fill[b][:]; null: off
+    const int* t_good = nullptr;
+    const float* fill = nullptr; long long fill_stride = 0;
     ClipState* state;                   // [B]
 };
 // TMA tensor maps of the tensor-core path (each an opaque 128-byte CUtensorMap; built on the host per problem)
 struct alignas(64) TcMapBlob { unsigned char b[128]; };
 struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXs, mapHs, mapHmn, mapHk, mapG, mapGlo; };
+
+constexpr int kSweepScalars = 136;   // per block of 8 coordinates: G diagonal block 8x8, look-ahead block 8x8, 1/diag (8)
 
 struct NmfWork {
     int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64, w_lanes = 1, w_rows = 128;
@@ -154,7 +166,11 @@ struct NmfWork {
     float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed (tf32 main-term operand), and its bf16 cross-term operand (tc::cross_pack8)
     float* tc_GLo = nullptr;                      // [B][KP][KP]: bf16 cross-term operand of W^T W
     float* tc_blobs = nullptr;                    // [B][KP/8][16*KP]: per-block update operands of the sweep (nmf_ts.cu: g_prep_kernel)
-    float* tc_scal = nullptr;                     // [B][KP/8][136]: per-block sweep scalars
+    float* tc_scal = nullptr;                     // [B][KP/8][kSweepScalars]: per-block sweep scalars
+    float* tc_vpartial = nullptr;                 // [B][nW][KP]: per-block shares of fill^T.W (good-first frame order)
+    float* tc_hbad = nullptr;                     // [B][KP]: sum of the bad frames' rows of Ht (good-first frame order)
+    float* tc_hbad_part = nullptr; int hbad_blocks = 1;   // [B][hbad_blocks][KP]: shares of tc_hbad
+    float* tc_vfill = nullptr;                    // [B][KP]: fill^T.W, the X^T.W row of every bad frame (good-first frame order)
     const TcMaps* tc = nullptr;
     float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
     float *violW = nullptr, *violH = nullptr;

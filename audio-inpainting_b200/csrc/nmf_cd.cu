@@ -259,6 +259,8 @@ template <int KP, int L_, int ROWS_> struct WSideCfg {
 struct WSideTc {                      // outputs for the tensor-core H step; all null on the FFMA path
     float* Wt; float* WtX; long long wt_stride; int ldw;
     float* GX; float* blobs; float* scal;
+    // good-first frame order: the bad frames' share of X.Ht is fill (x) hbad, and the H step needs v = fill^T.W
+    const float* fill; long long fill_stride; const float* hbad; float* vpartial; float* vfill;
 };
 template <int KP, int LANES, int NROWS>
 __global__ void __launch_bounds__(NROWS * LANES)
@@ -300,6 +302,16 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                         const float4 v = *reinterpret_cast<const float4*>(pr + 4 * q);
                         nb[q].x -= v.x; nb[q].y -= v.y; nb[q].z -= v.z; nb[q].w -= v.w;
                     }
+                }
+            }
+            if (valid && tc_out.hbad) {                    // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
+                const float fl = tc_out.fill[(long long)b * tc_out.fill_stride + f];
+                const float4* hb = reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP);
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const float4 v = hb[q];
+                    nb[q].x = fmaf(-fl, v.x, nb[q].x); nb[q].y = fmaf(-fl, v.y, nb[q].y);
+                    nb[q].z = fmaf(-fl, v.z, nb[q].z); nb[q].w = fmaf(-fl, v.w, nb[q].w);
                 }
             }
 #pragma unroll
@@ -364,6 +376,12 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                 const float4 v = *reinterpret_cast<const float4*>(pr + q);
                 g[q] -= v.x; g[q + 1] -= v.y; g[q + 2] -= v.z; g[q + 3] -= v.w;
             }
+        }
+        if (tc_out.hbad) {                                 // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
+            const float fl = tc_out.fill[(long long)b * tc_out.fill_stride + f];
+            const float* hb = tc_out.hbad + (long long)b * KP + l * SL;
+#pragma unroll
+            for (int q = 0; q < SL; ++q) g[q] = fmaf(-fl, hb[q], g[q]);
         }
     } else {
 #pragma unroll
@@ -439,6 +457,13 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         }
     }
 #endif
+    if (tc_out.vpartial) {
+        for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+            float acc = 0.f;
+            for (int rr = 0; rr < rows_here; ++rr) acc = fmaf(tc_out.fill[(long long)b * tc_out.fill_stride + f0 + rr], sA[rr * AP + k], acc);
+            tc_out.vpartial[((long long)b * P + blockIdx.x) * KP + k] = acc;
+        }
+    }
     // ---- this block's share of W^T W: thread (ty, tx) of a (THREADS/16) x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
     {
         constexpr int TY = Cfg::THREADS / 16, TI = KP / TY, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
@@ -517,6 +542,13 @@ w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P,
         __syncthreads();                                 // the rows just written are read back by other threads of the block
         g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
                      tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
+        if (threadIdx.x < 8) {                           // v[8blk + j] = fill^T.W: the X^T.W row of every bad frame
+            if (tc_out.vpartial) {
+                float v = 0.f;
+                for (int q = 0; q < P; ++q) v += tc_out.vpartial[((long long)b * P + q) * KP + 8 * blk + threadIdx.x];
+                tc_out.vfill[(long long)b * KP + 8 * blk + threadIdx.x] = v;
+            }
+        }
     }
 #endif
 }
@@ -798,6 +830,36 @@ static cudaError_t run_gram(const float* A, long long a_stride, int rows, int B,
     return cudaGetLastError();
 }
 
+// hbad[b][k] = sum over the bad frames t >= t_good[b] of Ht[b][t][k] (good-first frame order).  grid = (PB, B): block p sums
+// its contiguous share of the bad rows into part[b][p][:]; hbad_reduce_kernel adds the PB shares in order.
+__global__ void __launch_bounds__(kThreads)
+hbad_kernel(const float* __restrict__ Ht, long long h_stride, int T, int KP, const int* __restrict__ t_good, float* __restrict__ part,
+            const ClipState* __restrict__ st) {
+    __shared__ float s_acc[kThreads];
+    const int b = blockIdx.y, PB = gridDim.x;
+    if (st[b].done) return;
+    const int G = kThreads / KP, k = threadIdx.x % KP, gidx = threadIdx.x / KP;
+    const int t0 = t_good[b], per = (T - t0 + PB - 1) / PB;
+    const int lo = t0 + blockIdx.x * per, hi = min(T, lo + per);
+    float acc = 0.f;
+    for (int t = lo + gidx; t < hi; t += G) acc += Ht[(long long)b * h_stride + (long long)t * KP + k];
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    if (gidx == 0) {
+        float sum = 0.f;
+        for (int i = 0; i < G; ++i) sum += s_acc[i * KP + k];
+        part[((long long)b * PB + blockIdx.x) * KP + k] = sum;
+    }
+}
+__global__ void __launch_bounds__(128)
+hbad_reduce_kernel(const float* __restrict__ part, int PB, int KP, float* __restrict__ hbad, const ClipState* __restrict__ st) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (st[b].done || k >= KP) return;
+    float sum = 0.f;
+    for (int p = 0; p < PB; ++p) sum += part[((long long)b * PB + p) * KP + k];
+    hbad[(long long)b * KP + k] = sum;
+}
+
 template <int KP, int BM>
 static cudaError_t run_h_step(const NmfProblem& p, const NmfWork& wk, cudaStream_t s, float* xtw_out = nullptr) {
     using Cfg = HStepCfg<KP, BM>;
@@ -843,6 +905,12 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
         // tensor-core path: one kernel yields the X.Ht partials and the Gram of Ht
         prof_begin(PROF_XHT, s);
         if ((e = nmf_tc_half1(p, wk, s)) != cudaSuccess) return e;
+        if (p.t_good) {
+            AINMF_LAUNCH(hbad_kernel, dim3(wk.hbad_blocks, p.B), dim3(kThreads), 0, s, p.Ht, p.h_stride, p.T, KP, p.t_good, wk.tc_hbad_part,
+                         p.state);
+            AINMF_LAUNCH(hbad_reduce_kernel, dim3(p.B), dim3(128), 0, s, wk.tc_hbad_part, wk.hbad_blocks, KP, wk.tc_hbad, p.state);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
         prof_end(PROF_XHT, s);
         if (wk.xht_reduced) {
             const long long n4 = (long long)p.F * KP / 4;
@@ -869,8 +937,10 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     }
     if (phases & NMF_PHASE_UPDATE) {
         {
-            WSideTc tco{nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr};
-            if (wk.use_tc) tco = WSideTc{wk.tc_Wt, wk.tc_WtLo, (long long)KP * p.ldf, p.ldf, wk.tc_GLo, wk.tc_blobs, wk.tc_scal};
+            WSideTc tco{nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+            if (wk.use_tc) tco = WSideTc{wk.tc_Wt, wk.tc_WtLo, (long long)KP * p.ldf, p.ldf, wk.tc_GLo, wk.tc_blobs, wk.tc_scal,
+                                         p.t_good ? p.fill : nullptr, p.fill_stride, p.t_good ? wk.tc_hbad : nullptr,
+                                         p.t_good ? wk.tc_vpartial : nullptr, wk.tc_vfill};
             prof_begin(PROF_W_SWEEP, s);
             auto launch = [&](auto cfg) -> cudaError_t {
                 using WC = decltype(cfg);
@@ -1150,6 +1220,8 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
         wk->tc_fps = round_up(ceil_div(T, (int)sp), 32);
         wk->tc_splits = ceil_div(T, wk->tc_fps);
         wk->nH = ceil_div(T, 128);
+        long long hb = 2LL * n_sm / B;
+        wk->hbad_blocks = (int)(hb < 1 ? 1 : (hb > 64 ? 64 : hb));
     }
 #endif
 }
@@ -1163,7 +1235,8 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
     n += al256(sizeof(float) * (size_t)B * gp * KP * KP);                          // gram partials
     n += al256(sizeof(unsigned) * (size_t)B);                                      // counters
     n += al256(sizeof(float) * (size_t)B * (xs + 1) * F * KP);                      // xht partials
-    if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)) + al256(sizeof(float) * (size_t)B * KP * KP) + al256(sizeof(float) * (size_t)B * (KP / 8) * (16 * KP)) + al256(sizeof(float) * (size_t)B * (KP / 8) * 136); // Wt, Wt_lo, G_lo, sweep blobs + scalars
+    if (wk.use_tc) n += 2 * al256(sizeof(float) * (size_t)B * KP * round_up(F, 4)) + al256(sizeof(float) * (size_t)B * KP * KP) + al256(sizeof(float) * (size_t)B * (KP / 8) * (16 * KP)) + al256(sizeof(float) * (size_t)B * (KP / 8) * kSweepScalars) // Wt, Wt_lo, G_lo, sweep blobs + scalars
+                       + al256(sizeof(float) * (size_t)B * wk.nW * KP) + 2 * al256(sizeof(float) * (size_t)B * KP) + al256(sizeof(float) * (size_t)B * wk.hbad_blocks * KP); // fill^T.W partials, bad-frame sums of Ht, fill^T.W, hbad shares
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
     if (wk.want_mu) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
@@ -1186,7 +1259,11 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
         wk->tc_WtLo = (float*)take(sizeof(float) * (size_t)B * KP * round_up(F, 4));
         wk->tc_GLo = (float*)take(sizeof(float) * (size_t)B * KP * KP);
         wk->tc_blobs = (float*)take(sizeof(float) * (size_t)B * (KP / 8) * (16 * KP));
-        wk->tc_scal = (float*)take(sizeof(float) * (size_t)B * (KP / 8) * 136);
+        wk->tc_scal = (float*)take(sizeof(float) * (size_t)B * (KP / 8) * kSweepScalars);
+        wk->tc_vpartial = (float*)take(sizeof(float) * (size_t)B * wk->nW * KP);
+        wk->tc_hbad = (float*)take(sizeof(float) * (size_t)B * KP);
+        wk->tc_vfill = (float*)take(sizeof(float) * (size_t)B * KP);
+        wk->tc_hbad_part = (float*)take(sizeof(float) * (size_t)B * wk->hbad_blocks * KP);
     }
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);

@@ -98,7 +98,9 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGlo, int F, int T, int B,
                  const float* __restrict__ blobs /*[B][NBLK][16 KP]*/, const float* __restrict__ scal /*[B][NBLK][TS_SC]*/,
                  float* __restrict__ Ht, long long h_stride,
-                 float* __restrict__ viol /*[B][nH]*/, const ClipState* __restrict__ st, long long* __restrict__ dbg, int exp_flags) {
+                 float* __restrict__ viol /*[B][nH]*/, const ClipState* __restrict__ st, long long* __restrict__ dbg, int exp_flags,
+                 const int* __restrict__ t_good /*good-first frame order: frames >= t_good[b] are the identical bad ones; or null*/,
+                 const float* __restrict__ vfill /*[B][KP]: fill^T.W*/) {
     using Cfg = TsCfg<KP>;
     constexpr int NSS = Cfg::NSS, NAS = Cfg::NAS, NBLK = Cfg::NBLK, NG = Cfg::NG;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -114,6 +116,8 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int nk = nkX + KP / TS_BK;
     const bool dbg_on = dbg != nullptr && blockIdx.x == 0;
     const long long dbg_t0 = clock64();
+    // a tile that holds only bad frames needs no X chunks: its X^T.W rows are all fill^T.W, added by the sweep threads
+    auto first_chunk = [&](int bb, int mm) { return (t_good && mm * TS_M >= t_good[bb]) ? nkX : 0; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSS; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
@@ -141,7 +145,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             uint32_t it = 0;
             while (tiles.next(b, mt)) {
                 const int m0 = mt * TS_M;
-                for (int i = 0; i < nk; ++i, ++it) {
+                for (int i = first_chunk(b, mt); i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, ph = (it / NSS) & 1;
                     mbar_wait(&bars.empty[s], ph ^ 1);
                     unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
@@ -179,7 +183,8 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 tcgen05_fence_after();
                 if (dbg_on && tl < 64) dbg[8 * tl + 0] = clock64() - dbg_t0;
                 const uint32_t dcol = tmem + Cfg::COL_D + buf * KP;
-                for (int i = 0; i < nk; ++i, ++it) {
+                const int i0 = first_chunk(b, mt);
+                for (int i = i0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, a = it % NAS;
                     if (it >= TS_QD) mbar_wait(&bars.aempty[(it - TS_QD) % NAS], ((it - TS_QD) / NAS) & 1);
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
@@ -194,7 +199,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     for (int k8 = 0; k8 < TS_BK / 8; ++k8) {
                         if (k8 >= n8) break;
                         const uint64_t o = (uint64_t)(k8 * 32 >> 4);
-                        mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, idesc | ng, (i > 0 || k8 > 0) ? 1u : 0u);
+                        mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, idesc | ng, (i > i0 || k8 > 0) ? 1u : 0u);
                         mma_bf16_ts(dcol, acol + 32 + k8 * 8, d_bl + o, idesc16 | ng, 1);
                     }
                     mma_commit(&bars.empty[s]);
@@ -269,7 +274,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         long long k_full = 0, k_ae = 0, k_rd = 0, k_st = 0, k_t = 0;
         const bool kd = dbg_on && row == 0;
         while (tiles.next(b, mt)) {
-            for (int i = 0; i < nk; ++i, ++it) {
+            for (int i = first_chunk(b, mt); i < nk; ++i, ++it) {
                 const uint32_t s = it % NSS, a = it % NAS;
                 if (kd) k_t = clock64();
                 if (lane == 0) mbar_wait(&bars.full[s], (it / NSS) & 1);
@@ -331,6 +336,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const uint32_t buf = tl & 1;
             const int t = mt * TS_M + row;
             const bool valid = t < T;
+            const bool badrow = t_good && valid && t >= t_good[b];           // its X row is zero in the permuted copy: X^T.W row = fill^T.W
             float* hrow = Ht + (long long)b * h_stride + (long long)t * KP;
             if (lane == 0) {
                 mbar_wait(&bars.sfull[buf], (tl >> 1) & 1);
@@ -347,11 +353,21 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #define TS_TOC(acc) do { if (dbg_on) acc += clock64() - c_t; } while (0)
             TS_TIC();
             tmem_ld_32x8(tlane + Cfg::COL_D + buf * KP, d8);
+            const float* vrow = vfill + (long long)b * KP;
+            if (badrow) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(vrow)), v1 = __ldg(reinterpret_cast<const float4*>(vrow + 4));
+                d8[0] += v0.x; d8[1] += v0.y; d8[2] += v0.z; d8[3] += v0.w; d8[4] += v1.x; d8[5] += v1.y; d8[6] += v1.z; d8[7] += v1.w;
+            }
             TS_TOC(c_ld);
 #pragma unroll 1
             for (int blk = 0; blk < NBLK; ++blk) {
                 const float* gb = sc + blk * TS_SC;
                 float a8[8], dl[8];
+                float4 vn0 = make_float4(0.f, 0.f, 0.f, 0.f), vn1 = vn0;     // fill^T.W of the next block, fetched a block ahead
+                if (badrow && blk + 1 < NBLK) {
+                    vn0 = __ldg(reinterpret_cast<const float4*>(vrow + 8 * (blk + 1)));
+                    vn1 = __ldg(reinterpret_cast<const float4*>(vrow + 8 * (blk + 1) + 4));
+                }
                 const bool fd = dbg_on && row == 0 && tl == 2 && blk < 16;
 #define TS_STAMP(k) do { if (fd) dbg[8 * 66 + blk * 8 + (k)] = clock64() - dbg_t0; } while (0)
                 TS_STAMP(0);
@@ -409,6 +425,10 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     TS_STAMP(3);
                     TS_TIC();
                     tmem_ld_32x8(tlane + Cfg::COL_D + buf * KP + (blk + 1) * 8, d8);
+                    if (badrow) {
+                        d8[0] += vn0.x; d8[1] += vn0.y; d8[2] += vn0.z; d8[3] += vn0.w;
+                        d8[4] += vn1.x; d8[5] += vn1.y; d8[6] += vn1.z; d8[7] += vn1.w;
+                    }
                     TS_TOC(c_ld);
                     TS_STAMP(4);
                     if (blk + 2 == NBLK) {                            // last read of this accumulator, no update pending
@@ -504,7 +524,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__ CUtensorMap mapHs,
               const __grid_constant__ CUtensorMap mapHmn, int F, int T, int B, int S, int mtiles, int frames_per_split,
               float* __restrict__ xht_partial /*[B][S][F][KP]*/, float* __restrict__ gram_partial /*[B][S][KP][KP]*/,
-              const ClipState* __restrict__ st) {
+              const ClipState* __restrict__ st, const int* __restrict__ t_good /*good-first frame order or null*/) {
     using Cfg = XtCfg<KP>;
     constexpr int NSS = Cfg::NSS, NAS = Cfg::NAS, NB = KP / 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -528,17 +548,21 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
     const uint32_t tmem = tmem_slot;
     XtItems items{(int)blockIdx.x, (int)gridDim.x, B * S * mtiles, mtiles, S, st};
     int b, split, mt;
-    auto chunks_of = [&](int sp) {
+    // chunks of 32 frames of a work item; with the good-first frame order the X tiles stop at the last good frame (the
+    // permuted copy holds zeros beyond; the bad frames' share comes back as fill (x) hbad in the W-side kernel), the tile(s)
+    // that hold Ht columns (Gram) run over every frame
+    auto chunks_of = [&](int bb, int sp, int mm) {
         const int t_begin = sp * frames_per_split;
-        const int t_end = min(T, t_begin + frames_per_split);
-        return (t_end - t_begin + TS_BK - 1) / TS_BK;
+        int t_end = min(T, t_begin + frames_per_split);
+        if (t_good && 4 * mm + 3 < nxs) t_end = min(t_end, t_good[bb]);
+        return max(0, (t_end - t_begin + TS_BK - 1) / TS_BK);
     };
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             while (items.next(b, split, mt)) {
-                const int nk = chunks_of(split), t_begin = split * frames_per_split;
+                const int nk = chunks_of(b, split, mt), t_begin = split * frames_per_split;
                 for (int i = 0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS;
                     mbar_wait(&bars.empty[s], ((it / NSS) & 1) ^ 1);
@@ -564,7 +588,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
             const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 1), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
             uint32_t it = 0, tl = 0;
             while (items.next(b, split, mt)) {
-                const int nk = chunks_of(split);
+                const int nk = chunks_of(b, split, mt);
                 const uint32_t buf = tl & 1;
                 mbar_wait(&bars.dempty[buf], ((tl >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
@@ -595,7 +619,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_A;
         uint32_t it = 0;
         while (items.next(b, split, mt)) {
-            const int nk = chunks_of(split);
+            const int nk = chunks_of(b, split, mt);
             for (int i = 0; i < nk; ++i, ++it) {
                 const uint32_t s = it % NSS, a = it % NAS;
                 if (lane == 0) {
@@ -641,6 +665,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
         uint32_t tl = 0;
         while (items.next(b, split, mt)) {
             const uint32_t buf = tl & 1;
+            const bool empty_item = chunks_of(b, split, mt) == 0;           // nothing was accumulated: the partial is zero
             if (lane == 0) mbar_wait(&bars.dfull[buf], (tl >> 1) & 1);
             __syncwarp();
             tcgen05_fence_after();
@@ -655,6 +680,10 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
             for (int c0 = 0; c0 < KP; c0 += 32) {
                 float v[32];
                 tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_D + buf * KP + c0, v);
+                if (empty_item) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
                 if (dst) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -704,7 +733,7 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     AINMF_LAUNCH(h_step_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX), as_map(wk.tc->mapWt),
                  as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), as_map(wk.tc->mapGlo), p.F, p.T, p.B,
-                 wk.tc_blobs, wk.tc_scal, p.Ht, p.h_stride, wk.violH, p.state, dbg_left > 0 ? dbg : nullptr, exp_flags);
+                 wk.tc_blobs, wk.tc_scal, p.Ht, p.h_stride, wk.violH, p.state, dbg_left > 0 ? dbg : nullptr, exp_flags, p.t_good, wk.tc_vfill);
     if (dbg_left > 0) {
         --dbg_left;
         long long hbuf[8 * 84];
@@ -741,7 +770,7 @@ static cudaError_t ts_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     const long long items = (long long)p.B * wk.tc_splits * wk.tc_mtiles;
     const int grid = (int)(items < n_sm ? items : n_sm);
     AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
-                 as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state);
+                 as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state, p.t_good);
     return cudaGetLastError();
 }
 cudaError_t nmf_ts_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {

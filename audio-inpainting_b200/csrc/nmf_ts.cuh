@@ -1,11 +1,12 @@
 // nmf_ts.cuh -- pieces shared by the tensor-core kernels (nmf_ts.cu) and the W-side kernel (nmf_cd.cu).
 #pragma once
 #ifndef AINMF_EMU
+#include "kernels.h"
 #include "tc.cuh"
 
 namespace ainmf {
 
-constexpr int TS_SC = 136;           // floats of sweep scalars per block: G diagonal block 8x8, look-ahead block 8x8, 1/diag
+constexpr int TS_SC = kSweepScalars;  // floats of sweep scalars per block: G diagonal block 8x8, look-ahead block 8x8, 1/diag
 
 // Operands the H step derives from G = W^T W, for block `blk` of 8 coordinates of one clip (called by `nthreads`
 // threads with index `tid`):

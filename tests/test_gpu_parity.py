@@ -297,6 +297,49 @@ def test_c1_part0_golden(ops, golden):
 
 
 # ---- edge cases --------------------------------------------------------------------------------------------
+def test_good_first_frame_order_skips_bad_frames_exactly(ops):
+    """With enough tiles to fill the machine the fit runs on a good-first permutation of the frames and skips the bad
+    frames' share of both contractions (they are all the fill spectrum).  Same objective and waveform as without
+    it and as the oracle; clips with many, few and no bad frames in one batch.  (The factors themselves are not compared:
+    on this low-rank data H differs by 1e-4..1e-3 between ANY two summation orders, e.g. FFMA vs tensor path.)"""
+    import os
+    rng = np.random.default_rng(17)
+    B, N, sr = 32, 66150, 44100
+    t = np.arange(N) / sr
+    X = np.empty((B, N), np.float32)
+    for b in range(B):
+        f = rng.uniform(200, 6000, 5)
+        x = sum(np.sin(2 * np.pi * fi * t + rng.uniform(0, 6)) for fi in f) + 0.05 * rng.standard_normal(N)
+        x = (x / np.abs(x).max()).astype(np.float32)
+        if b % 3 == 0:
+            x[20000:20000 + 4000 * (1 + b % 5)] = 0            # one gap of 0.09 .. 0.45 s
+        elif b % 3 == 1:
+            for s0 in rng.integers(0, N - 3000, 6):
+                x[s0:s0 + int(rng.integers(600, 2500))] = 0     # scattered fragments
+        X[b] = x                                                # b % 3 == 2: nothing bad
+    args = (512, 128, 64, 30, 1e-4, 42, 1e-4, 9, 10, -1, -1, 1, None, None)
+    os.environ.pop("AINMF_NO_COMPACT", None)
+    y1, idx1, nb1, W1, H1, e1, n1 = ops.nmf_inpaint(dev(X), *args)
+    os.environ["AINMF_NO_COMPACT"] = "1"
+    try:
+        y0, idx0, nb0, W0, H0, e0, n0 = ops.nmf_inpaint(dev(X), *args)
+    finally:
+        os.environ.pop("AINMF_NO_COMPACT", None)
+    assert torch.equal(nb1, nb0) and torch.equal(idx1, idx0) and torch.equal(n1, n0)
+    assert int((nb1 > 0).sum()) >= 20 and int((nb1 == 0).sum()) >= 8
+    for b in range(B):
+        if int(nb1[b]) == 0:
+            assert torch.equal(y1[b], dev(X[b]))
+            continue
+        assert abs(float(e1[b]) - float(e0[b])) <= 1e-4 * float(e0[b])            # north_star tolerance on the objective
+        assert libcalls.snr_db(y0[b].cpu().numpy(), y1[b].cpu().numpy()) > 90.0
+    for b in (0, 1, 4):
+        yo, st = libcalls.restore_columns(X[b], sr, n_fft=512, hop=128, K=64, seed=42, max_iter=30, return_all=True)
+        assert int(nb1[b]) == len(st["bad"])
+        assert abs(float(e1[b]) - st["err"]) <= 1e-4 * st["err"]
+        assert libcalls.snr_db(yo, y1[b].cpu().numpy()) >= 60.0
+
+
 def test_no_bad_frames_returns_input(ops):
     rng = np.random.default_rng(1)
     x = (0.5 + 0.1 * rng.standard_normal((2, 30000))).astype(np.float32)
