@@ -682,10 +682,13 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     if (!h) return AINMF_ERR_INVALID;
     if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
     CU(h, cudaSetDevice(h->device));
+    // workspace per clip, estimated on a batch large enough to include what only big batches allocate (the permuted copy
+    // of the spectrogram for the good-first frame order)
     ainmf_params one = *p;
-    one.batch = 1;
-    const size_t per_clip_ws = ainmf_workspace_bytes(h, &one);
-    if (per_clip_ws == 0) return AINMF_ERR_INVALID;    // message set by make_plan
+    one.batch = p->batch < 256 ? p->batch : 256;
+    const size_t probe_ws = ainmf_workspace_bytes(h, &one);
+    if (probe_ws == 0) return AINMF_ERR_INVALID;       // message set by make_plan
+    const size_t per_clip_ws = (probe_ws + one.batch - 1) / one.batch;
     const long long N = p->n_samples;
     if (max_device_bytes == 0) {
 #ifndef AINMF_EMU
