@@ -488,7 +488,7 @@ def main():
                   "xht_gram_tc": "xht_ts_kernel (X.Ht contraction + Gram of Ht on tcgen05, one launch per iteration)",
                   "w_side_fused": "w_side_kernel"}.get(dom, dom)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     if os.path.exists(tpath) and args.workload == "c4":
         tj = json.load(open(tpath))
         key = {"h_step_tc": "h_step_ts_kernel", "xht_gram_tc": "xht_ts_kernel", "w_side_fused": "w_side_kernel"}.get(dom)

@@ -8,7 +8,7 @@ SMALL="--clips 64 --steps 1 --no-cpu-baseline"
 python bench.py > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err || { echo "bench failed"; tail -20 $OUT/bench_${TAG}.err; exit 1; }
 tail -c 2500 $OUT/bench_${TAG}.json
 python bench.py $SMALL > $OUT/plain_${TAG}.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'(h_step_ts|xht_ts|w_side|w_finish|gram|reduce_splits|stop|stft|istft|gap_mask|compact|colsum|colsum_reduce|fill|fill_rows|mean|init_w|init_h|finalize|err_reduce|transpose_h|unpack_w)_kernel' -s 0 -c 900 --csv --log-file $OUT/launches_${TAG}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'(h_step_ts|xht_ts|w_side|w_finish|hbad|hbad_reduce|gather_rows|scatter_rows|build_perm|invert_flags|gram|reduce_splits|stop|stft|istft|gap_mask|compact|colsum|colsum_reduce|fill|fill_rows|mean|init_w|init_h|finalize|err_reduce|transpose_h|unpack_w)_kernel' -s 0 -c 900 --csv --log-file $OUT/launches_${TAG}.csv \
     python bench.py $SMALL > $OUT/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
 python bench.py $SMALL > $OUT/plain2_${TAG}.log 2>&1 &&
