@@ -758,33 +758,67 @@ finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int 
     float* Xb = Xt + (long long)b * x_stride;
     const float* Wb = W + (long long)b * w_stride;
     double e2 = 0.0;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        float dot[FR];
+    // Two bins per thread share every H load (FMA : LDS.128 = 8 : 1); the bins past the last full round of
+    // blockDim.x (one bin for F = 2^m + 1) are spread over (bin, frame) pairs instead of idling all but a few threads.
+    const int Fmain = (F / (int)blockDim.x) * (int)blockDim.x;
+    for (int fb = 0; fb < Fmain; fb += 2 * blockDim.x) {
+        const int f0 = fb + threadIdx.x, f1 = f0 + blockDim.x;
+        const bool has1 = f1 < Fmain;                              // uniform across the block
+        float d0[FR], d1[FR];
 #pragma unroll
-        for (int r = 0; r < FR; ++r) dot[r] = 0.f;
-        const float* wr = Wb + (long long)f * KP;
+        for (int r = 0; r < FR; ++r) { d0[r] = 0.f; d1[r] = 0.f; }
+        const float* w0r = Wb + (long long)f0 * KP;
+        const float* w1r = Wb + (long long)(has1 ? f1 : f0) * KP;
         for (int k = 0; k < KP; k += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(wr + k);
+            const float4 w0 = *reinterpret_cast<const float4*>(w0r + k);
+            const float4 w1 = *reinterpret_cast<const float4*>(w1r + k);
 #pragma unroll
             for (int r = 0; r < FR; ++r) {
                 const float4 h = *reinterpret_cast<const float4*>(&sH[r][k]);
-                dot[r] = fmaf(w.x, h.x, dot[r]);
-                dot[r] = fmaf(w.y, h.y, dot[r]);
-                dot[r] = fmaf(w.z, h.z, dot[r]);
-                dot[r] = fmaf(w.w, h.w, dot[r]);
+                d0[r] = fmaf(w0.x, h.x, d0[r]);
+                d1[r] = fmaf(w1.x, h.x, d1[r]);
+                d0[r] = fmaf(w0.y, h.y, d0[r]);
+                d1[r] = fmaf(w1.y, h.y, d1[r]);
+                d0[r] = fmaf(w0.z, h.z, d0[r]);
+                d1[r] = fmaf(w1.z, h.z, d1[r]);
+                d0[r] = fmaf(w0.w, h.w, d0[r]);
+                d1[r] = fmaf(w1.w, h.w, d1[r]);
             }
         }
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < FR; ++r) {
             if (t0 + r < T) {
-                const long long o = (long long)(t0 + r) * ldf + f;
-                const float d = Xb[o] - dot[r];
+                const long long o = (long long)(t0 + r) * ldf + f0;
+                const float d = Xb[o] - d0[r];
                 s = fmaf(d, d, s);
-                if (s_bad[r]) Xb[o] = dot[r];
+                if (s_bad[r]) Xb[o] = d0[r];
+                if (has1) {
+                    const float e = Xb[o + blockDim.x] - d1[r];
+                    s = fmaf(e, e, s);
+                    if (s_bad[r]) Xb[o + blockDim.x] = d1[r];
+                }
             }
         }
         e2 += (double)s;
+    }
+    for (int i = threadIdx.x; i < (F - Fmain) * FR; i += blockDim.x) {
+        const int f = Fmain + i / FR, r = i % FR;
+        if (t0 + r >= T) continue;
+        const float* wr = Wb + (long long)f * KP;
+        float dot = 0.f;
+        for (int k = 0; k < KP; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + k);
+            const float4 h = *reinterpret_cast<const float4*>(&sH[r][k]);
+            dot = fmaf(w.x, h.x, dot);
+            dot = fmaf(w.y, h.y, dot);
+            dot = fmaf(w.z, h.z, dot);
+            dot = fmaf(w.w, h.w, dot);
+        }
+        const long long o = (long long)(t0 + r) * ldf + f;
+        const float d = Xb[o] - dot;
+        e2 += (double)(d * d);
+        if (s_bad[r]) Xb[o] = dot;
     }
     const double tot = block_sum_d(e2, s_red);
     if (threadIdx.x == 0) err_partial[(long long)b * gridDim.x + blockIdx.x] = tot;

@@ -141,20 +141,47 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
         return;
     }
 
-    for (int i = threadIdx.x; i < M; i += blockDim.x) s_twh[i] = tw_half[i];
-    for (int i = threadIdx.x; i <= M; i += blockDim.x) s_twf[i] = tw_full[i];
-    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) s_win[i] = window[i];
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) { s_out[i] = 0.f; s_nrm[i] = 0.f; }
-
     // frames c with c*hop <= e < c*hop + n_fft for some e = n + M, n in [s0, s_end)
     long long c_lo = (s0 + M - n_fft >= 0) ? (s0 + M - n_fft) / hop + 1 : 0;     // floor((e0-n_fft)/hop)+1
     long long c_hi = (s_end - 1 + M) / hop;
     if (c_hi > T_total - 1) c_hi = T_total - 1;
     if (c_lo < t_begin) c_lo = t_begin;                      // caller guarantees these are not needed
     if (c_hi > (long long)t_begin + t_count - 1) c_hi = (long long)t_begin + t_count - 1;
+    const unsigned char* badb = bad + (long long)b * bad_stride;
+
+    // No frame that reaches into this block's samples was modified: every such frame is the transform of x * w, so
+    // the windowed overlap-add returns x * sum(w^2) and the normalisation divides it out again (_spectral_py.py:
+    // 1892-1910).  Write x (times sum w^2 where scipy leaves the sum un-normalised) and skip the transforms.
+    if (x != nullptr) {
+        __shared__ int s_any;
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
+        int any = 0;
+        for (long long c = c_lo + threadIdx.x; c <= c_hi; c += blockDim.x) any |= badb[c - t_begin];
+        if (any) s_any = 1;
+        __syncthreads();
+        if (!s_any) {
+            const float* xb = x + (long long)b * x_stride;
+            for (long long n = s0 + threadIdx.x; n < s_end; n += blockDim.x) {
+                const long long e = n + M;
+                long long ca = (e - n_fft >= 0) ? (e - n_fft) / hop + 1 : 0;
+                long long cb = e / hop;
+                if (cb > T_total - 1) cb = T_total - 1;
+                float nr = 0.f;
+                for (long long c = ca; c <= cb; ++c) { const float w = window[e - c * hop]; nr += w * w; }
+                const float xv = xb[n - x_origin];
+                yb[n - n_begin] = (nr > 1e-10f) ? xv : xv * nr;
+            }
+            return;
+        }
+    }
+
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s_twh[i] = tw_half[i];
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) s_twf[i] = tw_full[i];
+    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) s_win[i] = window[i];
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) { s_out[i] = 0.f; s_nrm[i] = 0.f; }
     __syncthreads();
 
-    const unsigned char* badb = bad + (long long)b * bad_stride;
     const float inv_M = 1.0f / (float)M;
     for (long long c0 = c_lo; c0 <= c_hi; c0 += kStftFramesPerPass) {
         // half-length spectrum for the inverse: Zk[k] = E[k] + i O[k], conjugated so that the forward
