@@ -735,15 +735,16 @@ stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, 
 
 // =====================================================================================================
 // finalize: err^2 partial = sum (X - W Ht^T)^2 over a tile of frames; bad frames <- (W Ht^T) row
-// (a8 + a9: _nmf.py:1623 and main4_NMF_gap.py:65-68).  grid = (ceil(T/16), B)
+// (a8 + a9: _nmf.py:1623 and main4_NMF_gap.py:65-68).  grid = (ceil(T/kFinalizeFrames), B)
 // =====================================================================================================
+constexpr int kFinalizeFrames = 16;
 template <int KP>
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int T,
                 const float* __restrict__ W, long long w_stride, const float* __restrict__ Ht,
                 long long h_stride, const unsigned char* __restrict__ bad, long long bad_stride,
                 double* __restrict__ err_partial /*[B][gridDim.x]*/) {
-    constexpr int FR = 16;
+    constexpr int FR = kFinalizeFrames;
     __shared__ __align__(16) float sH[FR][KP];
     __shared__ unsigned char s_bad[FR];
     __shared__ double s_red[32];
@@ -769,6 +770,16 @@ finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int 
         for (int r = 0; r < FR; ++r) { d0[r] = 0.f; d1[r] = 0.f; }
         const float* w0r = Wb + (long long)f0 * KP;
         const float* w1r = Wb + (long long)(has1 ? f1 : f0) * KP;
+        // X is read before the products so that its DRAM latency hides behind them (the stores to bad frames
+        // below would otherwise order every load after the previous frame's store)
+        float x0[FR], x1[FR];
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+            const bool ok = t0 + r < T;
+            const long long o = (long long)(t0 + r) * ldf + f0;
+            x0[r] = ok ? Xb[o] : 0.f;
+            x1[r] = (ok && has1) ? Xb[o + blockDim.x] : 0.f;
+        }
         for (int k = 0; k < KP; k += 4) {
             const float4 w0 = *reinterpret_cast<const float4*>(w0r + k);
             const float4 w1 = *reinterpret_cast<const float4*>(w1r + k);
@@ -790,11 +801,11 @@ finalize_kernel(float* __restrict__ Xt, long long x_stride, int ldf, int F, int 
         for (int r = 0; r < FR; ++r) {
             if (t0 + r < T) {
                 const long long o = (long long)(t0 + r) * ldf + f0;
-                const float d = Xb[o] - d0[r];
+                const float d = x0[r] - d0[r];
                 s = fmaf(d, d, s);
                 if (s_bad[r]) Xb[o] = d0[r];
                 if (has1) {
-                    const float e = Xb[o + blockDim.x] - d1[r];
+                    const float e = x1[r] - d1[r];
                     s = fmaf(e, e, s);
                     if (s_bad[r]) Xb[o + blockDim.x] = d1[r];
                 }
@@ -1039,7 +1050,7 @@ cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaS
 template <int KP>
 static cudaError_t finalize_impl(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad,
                                  long long bad_stride, double* err_sq, cudaStream_t s) {
-    const int n = ceil_div(p.T, 16);
+    const int n = ceil_div(p.T, kFinalizeFrames);
     AINMF_LAUNCH(finalize_kernel<KP>, dim3(n, p.B), dim3(kThreads), 0, s, p.Xt, p.x_stride, p.ldf, p.F, p.T, p.W,
                  p.w_stride, p.Ht, p.h_stride, bad, bad_stride, wk.err_partial);
     cudaError_t e = cudaGetLastError();
