@@ -23,9 +23,10 @@ __device__ __forceinline__ float2* block_fft_forward(float2* a, float2* b, const
         const int per = M / R;                 // butterflies per sequence
         const int total = per * nfr;
         const int tstride = M / (Ns * R);
+        const int lper = 31 - __clz(per);      // per is a power of two
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            const int fr = idx / per;
-            const int j = idx - fr * per;
+            const int fr = idx >> lper;
+            const int j = idx & (per - 1);
             const int k = j & (Ns - 1);
             const float2* in = a + fr * M;
             float2* out = b + fr * M;

@@ -25,7 +25,7 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
             const float2* __restrict__ tw_full, const float* __restrict__ window, float scale,
             float* __restrict__ V, float2* __restrict__ Z, long long vz_stride) {
     AINMF_DYN_SMEM(smem_raw);
-    const int M = n_fft >> 1;
+    const int M = n_fft >> 1, lM = 31 - __clz(M);
     const int seg_len = (kStftFramesPerBlock - 1) * hop + n_fft;
     float2* s_twh = reinterpret_cast<float2*>(smem_raw);          // [M]
     float2* s_twf = s_twh + M;                                     // [M + 1] (+1 pad to keep 16B alignment below)
@@ -53,15 +53,15 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
         const int fbase = pass * kStftFramesPerPass;               // first frame (within block) of this pass
         // windowed frames -> half-length complex sequences z[j] = (xw[2j], xw[2j+1])
         for (int idx = threadIdx.x; idx < kStftFramesPerPass * M; idx += blockDim.x) {
-            const int q = idx / M, j = idx - q * M;
+            const int q = idx >> lM, j = idx & (M - 1);
             const float* fr = s_seg + (fbase + q) * hop;
             s_a[idx] = make_float2(fr[2 * j] * s_win[2 * j], fr[2 * j + 1] * s_win[2 * j + 1]);
         }
         __syncthreads();
         const float2* Zh = block_fft_forward(s_a, s_b, s_twh, M, kStftFramesPerPass);
         // X[k] = E[k] + e^{-2 pi i k/n} O[k],  E = (Z[k] + conj Z[M-k])/2,  O = (Z[k] - conj Z[M-k])/(2i)
-        for (int idx = threadIdx.x; idx < kStftFramesPerPass * ldf; idx += blockDim.x) {
-            const int q = idx / ldf, k = idx - q * ldf;
+        for (int q = 0; q < kStftFramesPerPass; ++q)
+        for (int k = threadIdx.x; k < ldf; k += blockDim.x) {
             const int lt = lt0 + fbase + q;
             if (lt >= t_count) continue;
             float2 X = make_float2(0.f, 0.f);
@@ -120,7 +120,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
              const float* __restrict__ window, float win_sum, float* __restrict__ y, long long y_stride,
              long long n_begin, long long n_count) {
     AINMF_DYN_SMEM(smem_raw);
-    const int M = n_fft >> 1;
+    const int M = n_fft >> 1, lM = 31 - __clz(M);
     const int tile = kIstftHopsPerBlock * hop;
     float2* s_twh = reinterpret_cast<float2*>(smem_raw);          // [M]
     float2* s_twf = s_twh + M;                                     // [M + 1]
@@ -128,7 +128,6 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
     float2* s_b = s_a + kStftFramesPerPass * M;                    // [FP][M]
     float* s_win = reinterpret_cast<float*>(s_b + kStftFramesPerPass * M);   // [n_fft]
     float* s_out = s_win + n_fft;                                  // [tile]
-    float* s_nrm = s_out + tile;                                   // [tile]
 
     const int b = blockIdx.y;
     const long long s0 = n_begin + (long long)blockIdx.x * tile;  // first clip sample of this block
@@ -179,7 +178,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
     for (int i = threadIdx.x; i < M; i += blockDim.x) s_twh[i] = tw_half[i];
     for (int i = threadIdx.x; i <= M; i += blockDim.x) s_twf[i] = tw_full[i];
     for (int i = threadIdx.x; i < n_fft; i += blockDim.x) s_win[i] = window[i];
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) { s_out[i] = 0.f; s_nrm[i] = 0.f; }
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) s_out[i] = 0.f;
     __syncthreads();
 
     const float inv_M = 1.0f / (float)M;
@@ -187,7 +186,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
         // half-length spectrum for the inverse: Zk[k] = E[k] + i O[k], conjugated so that the forward
         // routine computes the inverse transform.
         for (int idx = threadIdx.x; idx < kStftFramesPerPass * M; idx += blockDim.x) {
-            const int q = idx / M, k = idx - q * M;
+            const int q = idx >> lM, k = idx & (M - 1);
             const long long c = c0 + q;
             float2 out = make_float2(0.f, 0.f);
             if (c <= c_hi) {
@@ -217,25 +216,30 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
         for (int q = 0; q < kStftFramesPerPass; ++q) {
             const long long c = c0 + q;
             if (c <= c_hi) {   // uniform across the block
-                const long long base = c * hop - M - s0;       // tile offset of frame sample 0
+                const int base = (int)(c * hop - M - s0);      // tile offset of frame sample 0
                 for (int j = threadIdx.x; j < n_fft; j += blockDim.x) {
-                    const long long p = base + j;
+                    const int p = base + j;
                     if (p >= 0 && p < tile) {
                         const float2 z = zt[q * M + (j >> 1)];
                         float v = (j & 1) ? -z.y : z.x;
                         v = (v * inv_M) * win_sum;
-                        const float w = s_win[j];
-                        s_out[p] += v * w;
-                        s_nrm[p] += w * w;
+                        s_out[p] += v * s_win[j];
                     }
                 }
             }
             __syncthreads();
         }
     }
+    // sum of w^2 over the frames that cover a sample, in the order the frames were added
     for (long long n = s0 + threadIdx.x; n < s_end; n += blockDim.x) {
         const int p = (int)(n - s0);
-        const float nr = s_nrm[p];
+        const long long e = n + M;
+        long long ca = (e - n_fft >= 0) ? (e - n_fft) / hop + 1 : 0;
+        long long cb = e / hop;
+        if (ca < c_lo) ca = c_lo;
+        if (cb > c_hi) cb = c_hi;
+        float nr = 0.f;
+        for (long long c = ca; c <= cb; ++c) { const float w = s_win[e - c * hop]; nr += w * w; }
         yb[n - n_begin] = s_out[p] / (nr > 1e-10f ? nr : 1.0f);
     }
 }
@@ -243,7 +247,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
 static size_t istft_smem_bytes(int n_fft, int hop) {
     const int M = n_fft / 2;
     return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * M) +
-           sizeof(float) * (size_t)(n_fft + 2 * kIstftHopsPerBlock * hop);
+           sizeof(float) * (size_t)(n_fft + kIstftHopsPerBlock * hop);
 }
 
 cudaError_t launch_istft(const float* V, const float2* Z, long long vz_stride, const unsigned char* bad,
