@@ -350,6 +350,30 @@ def test_no_bad_frames_returns_input(ops):
     assert not np.array_equal(y[1].cpu().numpy(), x[1])
 
 
+def test_istft_blocks_without_modified_frames_return_the_input(ops):
+    """Overlap-add identity used by the inverse: where no modified frame reaches, the windowed overlap-add of
+    the unmodified frames is x * sum(w^2) and scipy divides by sum(w^2) (_spectral_py.py:1892-1910), so those samples
+    equal the input; everything else still matches the oracle's full inverse transform."""
+    sr, n, n_fft, hop = 16000, 160000, 1024, 256
+    rng = np.random.default_rng(5)
+    t = np.arange(n) / sr
+    x = (0.4 * np.sin(2 * np.pi * 330.0 * t) + 0.2 * np.sin(2 * np.pi * 1234.0 * t) + 0.02 * rng.standard_normal(n)).astype(np.float32)
+    x[70000:82000] = 0
+    x /= np.abs(x).max()
+    y, idx, nb, *_ = _run_columns(ops, x, rank=64, max_iter=20)
+    y = y[0].cpu().numpy()
+    bad = idx[0, :int(nb[0])].cpu().numpy()
+    lo, hi = int(bad.min()) * hop - n_fft // 2, int(bad.max()) * hop + n_fft // 2      # samples the bad frames cover
+    tile = 16 * hop                                                                     # kIstftHopsPerBlock * hop
+    far_lo, far_hi = (lo // tile) * tile - tile, (hi // tile + 2) * tile
+    assert far_lo > 0 and far_hi < n
+    assert np.array_equal(y[:far_lo], x[:far_lo]) and np.array_equal(y[far_hi:], x[far_hi:])
+    assert not np.array_equal(y[lo:hi], x[lo:hi])
+    yo = libcalls.restore_columns(x, sr, n_fft=n_fft, hop=hop, K=64, seed=42, max_iter=20)
+    assert libcalls.snr_db(yo, y) >= 60.0
+    assert libcalls.snr_db(yo[:far_lo], y[:far_lo]) >= 100.0        # round trip of the oracle vs the exact identity
+
+
 def test_invalid_arguments_raise(ops):
     import ainmf
     x = torch.zeros((1, 30000), device="cuda")
