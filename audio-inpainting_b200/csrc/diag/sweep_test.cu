@@ -1,8 +1,8 @@
 // sweep_test.cu -- diagnostic entry point ainmf_test_sweep_inc: runs cd_sweep_rows_inc<KP,8,4> (the sweep the
 // tensor-core h-step uses) on caller-provided A, G, B so that it can be compared with the reference sweep
 // (_cdnmf_fast.pyx:8-38) in isolation -- through the CPU emulator harness and on the GPU.  Not on the product path.
-#include "kernels.h"
-#include "nmf_cd.cuh"
+#include "../kernels.h"
+#include "../nmf_cd.cuh"
 
 namespace ainmf {
 

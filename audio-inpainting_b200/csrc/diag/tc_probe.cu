@@ -3,7 +3,7 @@
 // Exported as ainmf_tc_probe for tests/test_gpu_tc.py; not part of the inpainting path.
 #include <stdio.h>
 
-#include "tc.cuh"
+#include "../tc.cuh"
 
 #ifndef AINMF_EMU
 namespace ainmf {
@@ -193,62 +193,3 @@ extern "C" int ainmf_tc_probe_x(int mode, int split, int N, int Kd, const float*
 }
 #endif
 
-// ---- MMA issue/throughput microbenchmark (diagnostic): `iters` groups of `per` back-to-back tcgen05.mma on garbage
-// operands, timed with clock64 from first issue to the commit's arrival.  ts = 1: A from TMEM, else from shared.
-#ifndef AINMF_EMU
-namespace ainmf {
-using namespace tc;
-__global__ void __launch_bounds__(128)
-tc_mma_bench_kernel(int N, int ts, int iters, int per, int commit_each, long long* out) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5;
-    unsigned char* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(base)[i] = 1.0f;
-    fence_proxy_async_smem();
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (warp == 1) tmem_alloc(&tmem_slot, 512);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc_tf32(128, N, 0, 0);
-        const uint32_t idesc16 = make_idesc_bf16(128, N, 0, 0);
-        const uint64_t da = make_smem_desc(smem_u32(base), 16, 1024);
-        const uint64_t db = make_smem_desc(smem_u32(base) + 16384, 16, 1024);
-        uint32_t ph = 0;
-        const long long t0 = clock64();
-        long long t_issue = 0;
-        for (int it = 0; it < iters; ++it) {
-            for (int j = 0; j < per; ++j) {
-                const uint64_t o = (uint64_t)((j & 3) * 2);
-                if (ts == 1) mma_tf32_ts(tmem, tmem + 256 + (j & 3) * 8, db + o, idesc, 1);
-                else if (ts == 0) mma_tf32_ss(tmem, da + o, db + o, idesc, 1);
-                else if (ts == 3) mma_bf16_ts(tmem, tmem + 256 + (j & 3) * 8, db + o, idesc16, 1);
-                else mma_bf16_ss(tmem, da + o, db + o, idesc16, 1);
-            }
-            if (commit_each || it == iters - 1) {
-                if (it == iters - 1) t_issue = clock64() - t0;
-                mma_commit(&bar);
-                if (it == iters - 1 || commit_each == 2) { mbar_wait(&bar, ph); ph ^= 1; }
-            }
-        }
-        const long long t1 = clock64();
-        out[2 * blockIdx.x] = t1 - t0;
-        out[2 * blockIdx.x + 1] = t_issue;
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
-}
-}  // namespace ainmf
-extern "C" int ainmf_tc_mma_bench(int N, int ts, int iters, int per, int commit_each, int blocks, long long* out, void* stream) {
-    using namespace ainmf;
-    cudaError_t e = cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    tc_mma_bench_kernel<<<blocks, 128, 50 * 1024, (cudaStream_t)stream>>>(N, ts, iters, per, commit_each, out);
-    return (int)cudaGetLastError();
-}
-#endif

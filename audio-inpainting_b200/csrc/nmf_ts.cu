@@ -141,7 +141,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             while (tiles.next(b, mt)) {
                 const int m0 = mt * TS_M;
@@ -172,11 +172,11 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer: D[buf] = X_tile.W - Ht_tile.G ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 0), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
             const uint32_t neg = 1u << 13;                            // negate A
-            const int tail8 = (F - (nkX - 1) * TS_BK + 7) / 8;
             uint32_t it = 0, tl = 0;
+            long long q_ae = 0, q_full = 0, q_conv = 0, q_iss = 0, q_t = 0;
             while (tiles.next(b, mt)) {
                 const uint32_t buf = tl & 1;
                 mbar_wait(&bars.dempty[buf], ((tl >> 1) & 1) ^ 1);
@@ -186,35 +186,41 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const int i0 = first_chunk(b, mt);
                 for (int i = i0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, a = it % NAS;
+                    if (dbg_on) q_t = clock64();
                     if (it >= TS_QD) mbar_wait(&bars.aempty[(it - TS_QD) % NAS], ((it - TS_QD) / NAS) & 1);
+                    if (dbg_on) { const long long c = clock64(); q_ae += c - q_t; q_t = c; }
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
+                    if (dbg_on) { const long long c = clock64(); q_full += c - q_t; q_t = c; }
                     mbar_wait(&bars.conv[a], (it / NAS) & 1);
+                    if (dbg_on) { const long long c = clock64(); q_conv += c - q_t; q_t = c; }
                     tcgen05_fence_after();
                     const uint32_t ng = (i < nkX) ? 0u : neg;
                     const uint64_t d_bh = make_smem_desc(smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::X_BYTES), 16, 1024);
                     const uint64_t d_bl = d_bh + (uint64_t)(Cfg::B_BYTES >> 4);
                     const uint32_t acol = tmem + Cfg::COL_A + a * 64;
-                    const int n8 = (i == nkX - 1) ? tail8 : TS_BK / 8;      // the last X chunk may hold fewer than 32 bins
+                    // (the last X chunk may hold fewer than 32 bins: the TMA zero-fills the rest of both operands, and four
+                    //  straight-line instruction pairs issue faster than a loop with a data-dependent exit)
 #pragma unroll
                     for (int k8 = 0; k8 < TS_BK / 8; ++k8) {
-                        if (k8 >= n8) break;
                         const uint64_t o = (uint64_t)(k8 * 32 >> 4);
                         mma_tf32_ts(dcol, acol + k8 * 8, d_bh + o, idesc | ng, (i > i0 || k8 > 0) ? 1u : 0u);
                         mma_bf16_ts(dcol, acol + 32 + k8 * 8, d_bl + o, idesc16 | ng, 1);
                     }
                     mma_commit(&bars.empty[s]);
                     mma_commit(&bars.aempty[a]);
+                    if (dbg_on) q_iss += clock64() - q_t;
                 }
                 mma_commit(&bars.dfull[buf]);
                 if (dbg_on && tl < 64) dbg[8 * tl + 1] = clock64() - dbg_t0;
                 ++tl;
             }
+            if (dbg_on) { dbg[8 * 65 + 0] = q_ae; dbg[8 * 65 + 1] = q_full; dbg[8 * 65 + 2] = q_conv; dbg[8 * 65 + 3] = q_iss; dbg[8 * 65 + 4] = it; }
         }
     } else if (warp == 2) {
         // ---------------- sweep: loader of scalars / update operands + MMA issuer of D -= delta.G ----------------
         // Block blk of a tile needs an update MMA only if blk <= NBLK-3: the sweep threads themselves carry a block's
         // deltas into the NEXT block's 8 coordinates (look-ahead), so an update has one whole block of slack.
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idn = make_idesc_tf32(TS_M, KP, 0, 0) | (1u << 13), idn16 = make_idesc_bf16(TS_M, KP, 0, 0) | (1u << 13);
             TsTiles cur{(int)blockIdx.x, (int)gridDim.x, B * nH, nH, st};     // operand load cursor
             int cb = 0, cmt = 0, cblk = 0;
@@ -559,7 +565,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             while (items.next(b, split, mt)) {
                 const int nk = chunks_of(b, split, mt), t_begin = split * frames_per_split;
@@ -584,7 +590,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 1), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
             uint32_t it = 0, tl = 0;
             while (items.next(b, split, mt)) {
@@ -747,6 +753,8 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
             fprintf(stderr, "  tile 2 block %2d: start %lld coords +%lld store +%lld wait +%lld ld +%lld st +%lld lookahead +%lld\n", blk, q[0], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5]);
         }
         const long long* k = hbuf + 8 * 64;
+        const long long* qq = hbuf + 8 * 65;
+        if (qq[4]) fprintf(stderr, "  MMA issuer, cycles per chunk: wait A stage of chunk-%d done %lld, wait TMA %lld, wait converters %lld, issue 8 MMAs + 2 commits %lld  (%lld chunks)\n", TS_QD, qq[0] / qq[4], qq[1] / qq[4], qq[2] / qq[4], qq[3] / qq[4], qq[4]);
         if (k[4]) fprintf(stderr, "  converter thread 0, cycles per chunk: wait TMA %lld, wait A-stage free %lld, read+split %lld, tmem st+arrive %lld  (%lld chunks)\n", k[0] / k[4], k[1] / k[4], k[2] / k[4], k[3] / k[4], k[4]);
     }
     return cudaGetLastError();

@@ -47,6 +47,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp.  The single-thread roles (TMA producer, MMA issuers) must be entered as
+//     if (warp == ROLE) { if (elect_one()) { ... } }
+// and NOT as `if (lane == 0)`: tcgen05.mma / cp.async.bulk.tensor / tcgen05.commit are uniform-datapath instructions, and
+// when ptxas cannot prove that exactly one thread is active it wraps EVERY one of them in an ELECT + BRA.U.ANY
+// serialisation loop -- measured 127-160 cycles per tcgen05.mma whatever its shape, against 32 cycles for M128 N64
+// issued back to back (profiles/r02_mma_issue.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences -------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

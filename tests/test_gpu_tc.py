@@ -15,7 +15,8 @@ def trunc_tf32(a):
 
 def run_probe(mode, split, N, Kd, A, B):
     import ainmf
-    lib = ainmf._lib.lib()._handle if False else ainmf._lib.lib()
+    import diag
+    lib = diag.lib()
     fn = lib.ainmf_tc_probe
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -75,7 +76,8 @@ def test_probe_tf32_main_plus_bf16_cross_terms(N):
     bh = bf16_rn(np.ascontiguousarray(B)).reshape(N, g, 8)
     bl = bf16_rn(np.ascontiguousarray(Blo)).reshape(N, g, 8)
     Bx = np.concatenate([bh, bl], axis=2).reshape(N, g * 16).copy().view(np.float32).reshape(N, Kd)
-    lib = ainmf._lib.lib()
+    import diag
+    lib = diag.lib()
     fn = lib.ainmf_tc_probe_x
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1,8 +1,10 @@
+"""Developer helper (GPU): timing of the incremental coordinate sweep in isolation (csrc/diag/sweep_test.cu)."""
 import sys, os, ctypes as C
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import ainmf
-lib = ainmf._lib.lib(); ainmf._lib.handle(0)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import diag
+lib = diag.lib()
 fn = lib.ainmf_test_sweep_inc_timed
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1,8 +1,9 @@
+"""Developer helper (GPU): prints small tcgen05 probe outputs for operand-layout debugging."""
 import sys, os, ctypes as C
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from test_gpu_tc import run_probe
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_gpu_tc import run_probe  # noqa
 np.set_printoptions(linewidth=200, precision=1, suppress=True)
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 N, Kd = 64, 32
