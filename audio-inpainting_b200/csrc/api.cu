@@ -133,10 +133,13 @@ int fail(ainmf_handle h, int code, const char* fmt, ...) {
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 size_t al256(size_t n) { return (n + 255) / 256 * 256; }
 
-int check_fft(ainmf_handle h, int n_fft, int hop) {
+int check_fft(ainmf_handle h, int n_fft, int hop, bool forward = true, bool inverse = true) {
     if (!is_pow2(n_fft) || n_fft < 64 || n_fft > 4096) return fail(h, AINMF_ERR_INVALID, "n_fft must be a power of two in [64, 4096], got %d", n_fft);
     if (hop <= 0 || hop % 4 != 0 || n_fft % hop != 0 || n_fft / hop > 8 || n_fft / hop < 1)
         return fail(h, AINMF_ERR_INVALID, "hop must be a multiple of 4 that divides n_fft with n_fft/hop <= 8, got %d", hop);
+    if (stft_smem_need(n_fft, hop, forward, inverse) > 227 * 1024)
+        return fail(h, AINMF_ERR_INVALID, "n_fft %d with hop %d needs %zu bytes of shared memory per block (limit 232448): use a smaller hop",
+                    n_fft, hop, stft_smem_need(n_fft, hop, forward, inverse));
     return 0;
 }
 
@@ -270,7 +273,7 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     const int KP = pl->KP;
     impute_plan(T, &pl->iw);
     nmf_plan(B, T, F, KP, h->n_sm, &pl->nw);
-    if (p->solver == AINMF_SOLVER_MU) { pl->nw.want_mu = 1; pl->nw.use_tc = 0; }
+    if (p->solver == AINMF_SOLVER_MU) { pl->nw.want_mu = 1; pl->nw.use_tc = 0; pl->nw.exact_viol = 0; }
     pl->vz_stride = (long long)T * ldf;
     pl->bad_stride = round_up(T, 16);
     pl->w_stride = (long long)F * KP;
@@ -331,6 +334,18 @@ __global__ void status_summary_kernel(const ClipState* st, int B, int* out) {
     if (w) atomicAdd(&s_b, w);
     __syncthreads();
     if (threadIdx.x == 0) { out[1] = s_a; out[2] = s_b; }
+}
+
+// Clips whose every frame is flagged (status 2: the fill spectrum is the mean of an empty set, NaN in the reference) are
+// passed through: the inverse transform copies x when its frame count reads 0.  The exported n_bad stays T.
+__global__ void pass_through_all_bad_kernel(const ClipState* st, int B, int* n_bad_for_istft) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && st[b].status == 2) n_bad_for_istft[b] = 0;
+}
+
+__global__ void copy_indices_kernel(const int* __restrict__ idx, const ClipState* __restrict__ st, int T, int* __restrict__ out) {
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) out[(long long)b * T + t] = (t < st[b].n_bad) ? idx[(long long)b * T + t] : -1;
 }
 
 // Runs up to max_iter iterations, polling the stop flags every `poll` iterations when tol > 0.
@@ -425,7 +440,7 @@ int ainmf_stft(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples,
                float* mag_ft, float* Z_ft, void* stream) {
     if (!h) return AINMF_ERR_INVALID;
     if (!x || batch <= 0) return fail(h, AINMF_ERR_INVALID, "x is NULL or batch <= 0");
-    int rc = check_fft(h, n_fft, hop);
+    int rc = check_fft(h, n_fft, hop, true, false);
     if (rc) return rc;
     if (n_samples < n_fft) return fail(h, AINMF_ERR_INVALID, "n_samples (%lld) must be >= n_fft (%d)", (long long)n_samples, n_fft);
     StftGeom g;
@@ -483,7 +498,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     NmfWork nw;
     impute_plan(T, &iw);
     nmf_plan(B, T, F, KP, h->n_sm, &nw);
-    if (solver == AINMF_SOLVER_MU) { nw.want_mu = 1; nw.use_tc = 0; }
+    if (solver == AINMF_SOLVER_MU) { nw.want_mu = 1; nw.use_tc = 0; nw.exact_viol = 0; }
     const long long xs = (long long)T * ldf, ws = (long long)F * KP, hs = (long long)T * KP;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
@@ -531,7 +546,7 @@ int ainmf_istft(ainmf_handle h, const float* Z_ft, int32_t batch, int32_t T, int
                 int64_t n_samples, float* y, void* stream) {
     if (!h) return AINMF_ERR_INVALID;
     if (!Z_ft || !y || batch <= 0) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_istft");
-    int rc = check_fft(h, n_fft, hop);
+    int rc = check_fft(h, n_fft, hop, false, true);
     if (rc) return rc;
     StftGeom g;
     g.N = n_samples; g.n_fft = n_fft; g.hop = hop; g.T = T; g.F = n_fft / 2 + 1; g.ldf = round_up(g.F, 4);
@@ -642,7 +657,13 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(h->poll_host, d_flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
-    if (h->poll_host[1] > 0) return fail(h, AINMF_ERR_ALL_BAD, "%d clip(s) have every frame flagged: the fill spectrum is undefined", h->poll_host[1]);
+    // a single clip with every frame flagged fails like the reference does for that file; inside a batch such a clip is
+    // passed through (y = x, err = NaN, n_iter = 0, n_bad = T) and the other clips are restored
+    if (h->poll_host[1] > 0 && B == 1) return fail(h, AINMF_ERR_ALL_BAD, "every frame is flagged: the fill spectrum is undefined");
+    if (h->poll_host[1] > 0) {
+        AINMF_LAUNCH(pass_through_all_bad_kernel, dim3(ceil_div(B, kThreads)), dim3(kThreads), 0, s, st, B, d_nbad);
+        CU(h, cudaGetLastError());
+    }
     const bool any_work = h->poll_host[2] > 0;
     if (any_work) {
         const float *Wn = nullptr, *Hn = nullptr;
@@ -671,7 +692,10 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     }
     // a10 + a11: recombine with the corrupted phase, inverse STFT, trim
     CU(h, launch_istft(V, Z, pl.vz_stride, bad, pl.bad_stride, d_nbad, x, N, 0, B, g, 0, T, tb, y, N, 0, N, T, s));
-    if (bad_idx) CU(h, cudaMemcpyAsync(bad_idx, idx, sizeof(int) * (size_t)B * T, cudaMemcpyDeviceToDevice, s));
+    if (bad_idx) {          // entries at and beyond n_bad are -1, whatever the workspace held
+        AINMF_LAUNCH(copy_indices_kernel, dim3(ceil_div(T, kThreads), B), dim3(kThreads), 0, s, idx, st, T, bad_idx);
+        CU(h, cudaGetLastError());
+    }
     CU(h, launch_export_state(st, B, n_bad, n_iter, err, nullptr, s));
     if (any_work) CU(h, launch_unpack_factors(pr.W, pr.w_stride, pr.Ht, pr.h_stride, B, F, T, K, KP, W, H, s));
     return AINMF_OK;

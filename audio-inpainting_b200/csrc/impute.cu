@@ -269,8 +269,8 @@ export_state_kernel(const ClipState* __restrict__ st, int B, int* n_bad, int* n_
     if (b >= B) return;
     const ClipState s = st[b];
     if (n_bad) n_bad[b] = s.n_bad;
-    if (n_iter) n_iter[b] = s.n_iter;
-    if (err) err[b] = s.err;
+    if (n_iter) n_iter[b] = (s.status == 0) ? s.n_iter : 0;
+    if (err) err[b] = (s.status == 2) ? __int_as_float(0x7fc00000) : s.err;       // every frame flagged: NaN, as in the reference
     if (status) status[b] = s.status;
 }
 cudaError_t launch_export_state(const ClipState* st, int B, int* n_bad, int* n_iter, float* err, int* status,

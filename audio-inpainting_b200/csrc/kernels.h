@@ -28,6 +28,9 @@ cudaError_t launch_stft(const float* x, long long x_stride, long long x_origin, 
                         int t_begin, int t_count, const FftTables& tb, float* V, float2* Z,
                         long long vz_stride, cudaStream_t s);
 
+// dynamic shared memory per block that the forward and / or inverse kernel needs for this geometry
+size_t stft_smem_need(int n_fft, int hop, bool forward, bool inverse);
+
 // y[b][n] for n in [n_begin, n_begin + n_count): inverse STFT with overlap-add of Z' where
 // Z'[t] = bad[t] ? V[t] * Z[t]/|Z[t]| : Z[t].  Frames are local indices [0, t_count) that correspond
 // to global frames [t_begin, t_begin + t_count); frames outside contribute nothing (caller adds halos).
@@ -174,6 +177,10 @@ struct NmfWork {
     const TcMaps* tc = nullptr;
     float *HHt = nullptr, *WtW = nullptr, *gram_partial = nullptr, *xht_partial = nullptr;
     float *violW = nullptr, *violH = nullptr;
+    // small problems on the FFMA path (the early-stopping refit loop of main4_NMF.py): |pg| of every (row, coordinate) so that
+    // the stop rule can add them in sklearn's own order and precision when the decision is close (stop_kernel)
+    int exact_viol = 0;
+    float *pgW = nullptr, *pgH = nullptr;   // [B][F][KP], [B][T][KP]
     unsigned* counters = nullptr;       // must be zero before the first iteration
     double* err_partial = nullptr;
     // time-frame-sharded mode only (B == 1); null otherwise

@@ -45,10 +45,11 @@ template <int TN> __device__ __forceinline__ void load_frag(const float* row, in
 // Returns this lane's share of the violation.
 // sInv (optional): sInv[t] = 1 / G[t,t] (0 where the diagonal is 0); when given, the update multiplies by the
 // reciprocal instead of dividing (one rounding of difference per update; takes the division off the serial chain).
+// pg_row (optional): the owner lane of coordinate t stores |pg| to pg_row[t] (exact-order violation sum, stop_kernel).
 template <int KP, int L>
 __device__ __forceinline__ float cd_sweep_row(float (&a)[KP / L], const float (&bv)[KP / L],
                                               const float* __restrict__ sG, int l, bool valid,
-                                              const float* __restrict__ sInv = nullptr) {
+                                              const float* __restrict__ sInv = nullptr, float* __restrict__ pg_row = nullptr) {
     constexpr int S = KP / L;
     constexpr int PITCH = KP + 4 * L;
     float viol = 0.f;
@@ -82,12 +83,14 @@ __device__ __forceinline__ float cd_sweep_row(float (&a)[KP / L], const float (&
                 const float inv = sInv[t];
                 if (l == o && valid) {
                     viol += fabsf(pg);
+                    if (pg_row) pg_row[t] = fabsf(pg);
                     if (inv != 0.f) a[q] = fmaxf(fmaf(-grad, inv, aq), 0.f);
                 }
             } else {
                 const float hess = sG[t * PITCH + o * (S + 4) + q];
                 if (l == o && valid) {
                     viol += fabsf(pg);
+                    if (pg_row) pg_row[t] = fabsf(pg);
                     if (hess != 0.f) a[q] = fmaxf(aq - grad / hess, 0.f);
                 }
             }

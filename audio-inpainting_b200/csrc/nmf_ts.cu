@@ -23,10 +23,13 @@
 // D -= delta[128x8].G[8xKP], is an error-compensated K = 8 tensor-core MMA whose A operand (delta) the sweep threads
 // store straight into TMEM.
 //
-// Warp roles (384 threads, one CTA per SM, grid = min(#SM, #tiles), tiles round-robin):
+// Warp roles (K = 64: 512 threads; K = 128: one converter group, 384 threads; one CTA per SM, grid = min(#SM, #tiles), tiles round-robin):
 //   warp 0: TMA producer        warp 1: MMA issuer of the contraction (+ TMEM owner)
 //   warp 2: MMA issuer of the sweep updates + loader of the per-block Gram operands      warp 3: idle
-//   warps 4-7: converters (thread = frame = TMEM lane)      warps 8-11: sweep (thread = frame = TMEM lane)
+//   warps 4-7 and 8-11: two converter groups that take alternate chunks (thread = frame = TMEM lane): a converter's
+//       chunk costs two mbarrier waits (>= 90 cycles each, even when already complete) + the split + tcgen05.st, ~800
+//       cycles, against the ~670 cycles the chunk's 16 KB of X take at full HBM rate -- one group could not keep up
+//   warps 12-15: sweep (thread = frame = TMEM lane)
 #include "kernels.h"
 #include <stdlib.h>
 
@@ -39,8 +42,13 @@ using namespace tc;
 
 constexpr int TS_BK = 32;            // contraction elements per stage (one 128-byte row)
 constexpr int TS_M = 128;            // frames per tile = MMA M = TMEM lanes
-constexpr int TS_THREADS = 384;
-constexpr int TS_QD = 2;             // contraction chunks allowed in the tensor pipe at once (bounds the latency of a sweep update)
+// converter groups (4 warps each, alternate chunks): two at K = 64; at K = 128 the second group's gain in the contraction is
+// lost again in the sweep and the epilogue, which get 128 instead of 168 registers per thread in a 512-thread CTA (measured)
+template <int KP> struct TsShape {
+    static constexpr int CONV_GROUPS = (KP == 64) ? 2 : 1;
+    static constexpr int SWEEP_WARP0 = 4 + 4 * CONV_GROUPS;      // first sweep / epilogue warp
+    static constexpr int THREADS = 32 * (SWEEP_WARP0 + 4);
+};
 
 template <int KP> struct TsCfg {
     static constexpr int NSS = (KP == 64) ? 6 : 4;               // shared-memory stages (X chunk + W^T hi/lo chunk)
@@ -54,8 +62,8 @@ template <int KP> struct TsCfg {
     static constexpr int BLOB_BYTES = BLOB_FLOATS * 4;
     static constexpr int SC_BYTES = NBLK * TS_SC * 4;            // sweep scalars of one clip
     static constexpr int SMEM_BYTES = NSS * STAGE_BYTES + NG * BLOB_BYTES + 2 * SC_BYTES + 1024;
-    // TMEM columns: two accumulators, the delta operand of the sweep (hi 8 | lo 8), the A stages (hi 32 | lo 32)
-    static constexpr int COL_D = 0, COL_DELTA = 2 * KP, COL_A = 2 * KP + 16;
+    // TMEM columns: two accumulators, two slots of the sweep's delta operand (hi 8 | lo 8), the A stages (hi 32 | lo 32)
+    static constexpr int COL_D = 0, COL_DELTA = 2 * KP, COL_A = 2 * KP + 32;
     static_assert(COL_A + NAS * 64 <= 512, "TMEM budget");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -64,7 +72,7 @@ struct TsBarriers {
     uint64_t full[6], empty[6];      // shared-memory stage: TMA landed / MMA finished reading W^T chunk
     uint64_t conv[5], aempty[5];     // TMEM A stage: converters done / MMA finished reading it
     uint64_t dfull[2], dempty[2];    // accumulator: contraction complete / sweep has read its last block
-    uint64_t dready, ddone;          // sweep: delta block stored in TMEM / rank-8 update complete
+    uint64_t dready[2], ddone[2];    // sweep, per delta slot (block & 1): delta block stored in TMEM / rank-8 update complete
     uint64_t gfull[4], gempty[4];    // update operand ring: blob landed / update MMA finished reading it
     uint64_t sfull[2], sempty[2];    // sweep scalars of the tile's clip: landed / tile swept
 };
@@ -92,7 +100,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 __device__ __forceinline__ void sweep_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int KP>
-__global__ void __launch_bounds__(TS_THREADS, 1)
+__global__ void __launch_bounds__(TsShape<KP>::THREADS, 1)
 h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWt,
                  const __grid_constant__ CUtensorMap mapWtLo, const __grid_constant__ CUtensorMap mapHk,
                  const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGlo, int F, int T, int B,
@@ -123,8 +131,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int s = 0; s < NSS; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
         for (int a = 0; a < NAS; ++a) { mbar_init(&bars.conv[a], 4); mbar_init(&bars.aempty[a], 1); }
         for (int j = 0; j < 2; ++j) { mbar_init(&bars.dfull[j], 1); mbar_init(&bars.dempty[j], 4); }
-        mbar_init(&bars.dready, 4);
-        mbar_init(&bars.ddone, 1);
+        for (int j = 0; j < 2; ++j) { mbar_init(&bars.dready[j], 4); mbar_init(&bars.ddone[j], 1); }
         for (int j = 0; j < NG; ++j) { mbar_init(&bars.gfull[j], 1); mbar_init(&bars.gempty[j], 1); }
         for (int j = 0; j < 2; ++j) { mbar_init(&bars.sfull[j], 1); mbar_init(&bars.sempty[j], 4); }
         mbar_fence_init();
@@ -186,13 +193,13 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const int i0 = first_chunk(b, mt);
                 for (int i = i0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, a = it % NAS;
+                    // conv[a] first: the converters waited for full[s] themselves, so the second wait finds its phase
+                    // complete.  At most NAS chunks are in the tensor pipe (an A stage is recycled when its MMAs finish).
                     if (dbg_on) q_t = clock64();
-                    if (it >= TS_QD) mbar_wait(&bars.aempty[(it - TS_QD) % NAS], ((it - TS_QD) / NAS) & 1);
-                    if (dbg_on) { const long long c = clock64(); q_ae += c - q_t; q_t = c; }
-                    mbar_wait(&bars.full[s], (it / NSS) & 1);
-                    if (dbg_on) { const long long c = clock64(); q_full += c - q_t; q_t = c; }
                     mbar_wait(&bars.conv[a], (it / NAS) & 1);
                     if (dbg_on) { const long long c = clock64(); q_conv += c - q_t; q_t = c; }
+                    mbar_wait(&bars.full[s], (it / NSS) & 1);
+                    if (dbg_on) { const long long c = clock64(); q_full += c - q_t; q_t = c; }
                     tcgen05_fence_after();
                     const uint32_t ng = (i < nkX) ? 0u : neg;
                     const uint64_t d_bh = make_smem_desc(smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::X_BYTES), 16, 1024);
@@ -257,23 +264,25 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     refill();
                     const uint32_t slot = g % NG;
                     mbar_wait(&bars.gfull[slot], (g / NG) & 1);
-                    mbar_wait(&bars.dready, g & 1);
+                    mbar_wait(&bars.dready[g & 1], (g >> 1) & 1);
                     tcgen05_fence_after();
                     const uint32_t bh = smem_u32(sblob + (size_t)slot * Cfg::BLOB_BYTES);
                     // K-major, no swizzle: 8-row core matrices 128 B apart along N (SBO), K-adjacent cores KP*16 B apart (LBO)
                     const uint64_t d_gh = make_smem_desc(bh, KP * 16, 128, 0);
                     const uint64_t d_gl = make_smem_desc(bh + 8 * KP * 4, KP * 16, 128, 0);
-                    mma_tf32_ts(dcol, tmem + Cfg::COL_DELTA, d_gh, idn, 1);
-                    mma_bf16_ts(dcol, tmem + Cfg::COL_DELTA + 8, d_gl, idn16, 1);
-                    mma_commit(&bars.ddone);
+                    mma_tf32_ts(dcol, tmem + Cfg::COL_DELTA + 16 * (g & 1), d_gh, idn, 1);
+                    mma_bf16_ts(dcol, tmem + Cfg::COL_DELTA + 16 * (g & 1) + 8, d_gl, idn16, 1);
+                    mma_commit(&bars.ddone[g & 1]);
                     mma_commit(&bars.gempty[slot]);
                 }
                 ++tl;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ---------------- converters: shared X chunk -> (hi, lo) -> TMEM A stage ----------------
+    } else if (warp >= 4 && warp < TsShape<KP>::SWEEP_WARP0) {
+        // ---------------- converters: shared X chunk -> (hi, lo) -> TMEM A stage; group 0 takes the even chunks ----------------
         const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t grp = (warp - 4) >> 2;
+        constexpr uint32_t gmask = TsShape<KP>::CONV_GROUPS - 1;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_A;
         const int sw = row & 7;
         uint32_t it = 0;
@@ -281,6 +290,7 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const bool kd = dbg_on && row == 0;
         while (tiles.next(b, mt)) {
             for (int i = first_chunk(b, mt); i < nk; ++i, ++it) {
+                if ((it & gmask) != grp) continue;
                 const uint32_t s = it % NSS, a = it % NAS;
                 if (kd) k_t = clock64();
                 if (lane == 0) mbar_wait(&bars.full[s], (it / NSS) & 1);
@@ -309,11 +319,11 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
         }
         if (kd) { dbg[8 * 64 + 0] = k_full; dbg[8 * 64 + 1] = k_ae; dbg[8 * 64 + 2] = k_rd; dbg[8 * 64 + 3] = k_st; dbg[8 * 64 + 4] = it; }
-    } else if (warp >= 8) {
+    } else if (warp >= TsShape<KP>::SWEEP_WARP0) {
         // ---------------- sweep: thread = frame ----------------
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t tl = 0, mc = 0;
+        uint32_t tl = 0, ug = 0, wc = 0;      // tiles, update requests, update waits
         // The old values of this thread's Ht row are fetched PD blocks ahead of their use, across tile boundaries: under
         // the contraction's TMA stream a global load takes thousands of cycles, and the sweep is a serial chain.
         constexpr int PD = 4;
@@ -422,8 +432,8 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     // the next block's accumulator columns: every update up to block blk-1 must have landed ...
                     if (blk >= 1) {
                         TS_TIC();
-                        if (lane == 0) mbar_wait(&bars.ddone, mc & 1);
-                        ++mc;
+                        if (lane == 0) mbar_wait(&bars.ddone[wc & 1], (wc >> 1) & 1);
+                        ++wc;
                         __syncwarp();
                         tcgen05_fence_after();
                         TS_TOC(c_dd);
@@ -447,11 +457,12 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         for (int j = 0; j < 8; ++j) hl[j] = dl[j];
                         cross_pack8(dl, hl + 8, true);
                         TS_TIC();
-                        tmem_st_32x16(tlane + Cfg::COL_DELTA, hl);
+                        tmem_st_32x16(tlane + Cfg::COL_DELTA + 16 * (ug & 1), hl);
                         tmem_wait_st();
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars.dready);
+                        if (lane == 0) mbar_arrive(&bars.dready[ug & 1]);
+                        ++ug;
                         TS_TOC(c_st);
                     }
                     TS_STAMP(5);
@@ -526,7 +537,7 @@ struct XtItems {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(TS_THREADS, 1)
+__global__ void __launch_bounds__(TsShape<KP>::THREADS, 1)
 xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__ CUtensorMap mapHs,
               const __grid_constant__ CUtensorMap mapHmn, int F, int T, int B, int S, int mtiles, int frames_per_split,
               float* __restrict__ xht_partial /*[B][S][F][KP]*/, float* __restrict__ gram_partial /*[B][S][KP][KP]*/,
@@ -601,8 +612,8 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                 const uint32_t dcol = tmem + Cfg::COL_D + buf * KP;
                 for (int i = 0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, a = it % NAS;
+                    mbar_wait(&bars.conv[a], (it / NAS) & 1);       // the converters waited for full[s] themselves
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
-                    mbar_wait(&bars.conv[a], (it / NAS) & 1);
                     tcgen05_fence_after();
                     const uint32_t b_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
                     const uint64_t d_bx = make_smem_desc(b_raw + 2 * Cfg::B_BYTES, 16, 1024);
@@ -620,13 +631,16 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                 ++tl;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < TsShape<KP>::SWEEP_WARP0) {
+        // two converter groups (warps 4-7, 8-11) take alternate chunks, as in the H step
         const int q = warp & 3, col = q * 32 + lane;
+        const uint32_t grp = (warp - 4) >> 2;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_A;
         uint32_t it = 0;
         while (items.next(b, split, mt)) {
             const int nk = chunks_of(b, split, mt);
             for (int i = 0; i < nk; ++i, ++it) {
+                if ((it & (uint32_t)(TsShape<KP>::CONV_GROUPS - 1)) != grp) continue;
                 const uint32_t s = it % NSS, a = it % NAS;
                 if (lane == 0) {
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
@@ -665,7 +679,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                 if (lane == 0) mbar_arrive(&bars.conv[a]);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= TsShape<KP>::SWEEP_WARP0) {
         // ---------------- epilogue: rows of the accumulator straight to the partial buffers ----------------
         const int q = warp & 3;
         uint32_t tl = 0;
@@ -737,7 +751,7 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     const int nH = ceil_div(p.T, TS_M);
     const long long tiles = (long long)p.B * nH;
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-    AINMF_LAUNCH(h_step_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX), as_map(wk.tc->mapWt),
+    AINMF_LAUNCH(h_step_ts_kernel<KP>, dim3(grid), dim3(TsShape<KP>::THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapX), as_map(wk.tc->mapWt),
                  as_map(wk.tc->mapWtLo), as_map(wk.tc->mapHk), as_map(wk.tc->mapG), as_map(wk.tc->mapGlo), p.F, p.T, p.B,
                  wk.tc_blobs, wk.tc_scal, p.Ht, p.h_stride, wk.violH, p.state, dbg_left > 0 ? dbg : nullptr, exp_flags, p.t_good, wk.tc_vfill);
     if (dbg_left > 0) {
@@ -750,11 +764,11 @@ static cudaError_t ts_hstep_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
             fprintf(stderr, "  tile %2d: mma %8lld .. %8lld   sweep %8lld .. %8lld   (tmem ld %lld, delta st+arrive %lld, update wait %lld)\n", i, hbuf[8 * i], hbuf[8 * i + 1], hbuf[8 * i + 2], hbuf[8 * i + 3], hbuf[8 * i + 4], hbuf[8 * i + 5], hbuf[8 * i + 6]);
         for (int blk = 0; blk < KP / 8; ++blk) {
             const long long* q = hbuf + 8 * 66 + 8 * blk;
-            fprintf(stderr, "  tile 2 block %2d: start %lld coords +%lld store +%lld wait +%lld ld +%lld st +%lld lookahead +%lld\n", blk, q[0], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5]);
+            fprintf(stderr, "  tile 2 block %2d: start %lld coords +%lld store +%lld wait +%lld ld +%lld st +%lld lookahead +%lld\n", blk, q[0], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5]);   // coords | store | delta st issue | update wait | ld issue + look-ahead | st visible + ld arrive
         }
         const long long* k = hbuf + 8 * 64;
         const long long* qq = hbuf + 8 * 65;
-        if (qq[4]) fprintf(stderr, "  MMA issuer, cycles per chunk: wait A stage of chunk-%d done %lld, wait TMA %lld, wait converters %lld, issue 8 MMAs + 2 commits %lld  (%lld chunks)\n", TS_QD, qq[0] / qq[4], qq[1] / qq[4], qq[2] / qq[4], qq[3] / qq[4], qq[4]);
+        if (qq[4]) fprintf(stderr, "  MMA issuer, cycles per chunk: (unused %lld) wait TMA %lld, wait converters %lld, issue 8 MMAs + 2 commits %lld  (%lld chunks)\n", qq[0] / qq[4], qq[1] / qq[4], qq[2] / qq[4], qq[3] / qq[4], qq[4]);
         if (k[4]) fprintf(stderr, "  converter thread 0, cycles per chunk: wait TMA %lld, wait A-stage free %lld, read+split %lld, tmem st+arrive %lld  (%lld chunks)\n", k[0] / k[4], k[1] / k[4], k[2] / k[4], k[3] / k[4], k[4]);
     }
     return cudaGetLastError();
@@ -777,7 +791,7 @@ static cudaError_t ts_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     }
     const long long items = (long long)p.B * wk.tc_splits * wk.tc_mtiles;
     const int grid = (int)(items < n_sm ? items : n_sm);
-    AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(TS_THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
+    AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(TsShape<KP>::THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
                  as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state, p.t_good);
     return cudaGetLastError();
 }

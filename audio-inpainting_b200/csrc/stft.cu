@@ -244,6 +244,11 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
     }
 }
 
+static size_t istft_smem_bytes(int n_fft, int hop);
+size_t stft_smem_need(int n_fft, int hop, bool forward, bool inverse) {
+    const size_t a = forward ? stft_smem_bytes(n_fft, hop) : 0, b = inverse ? istft_smem_bytes(n_fft, hop) : 0;
+    return a > b ? a : b;
+}
 static size_t istft_smem_bytes(int n_fft, int hop) {
     const int M = n_fft / 2;
     return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * M) +

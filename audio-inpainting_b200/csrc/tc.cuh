@@ -115,6 +115,21 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same without the wait: the caller overlaps independent work and calls tmem_wait_ld() before reading r[]
+__device__ __forceinline__ void tmem_ld_32x8_async(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// r[] must be passed through so that the compiler cannot move their first use above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+
 // thread i of the warp writes v[j] to lane (base_lane + i), column (base_col + j); no wait (see tmem_wait_st)
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const float (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

@@ -1,14 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- audio-seconds restored per second on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c5|c1|c2|c3] [--legs ...]
 
-Default workload ("c4", BASELINE.json configs[3]): a batch of 10 s / 44.1 kHz clips with random-fragment masks
+Headline workload ("c4", BASELINE.json configs[3]): a batch of 10 s / 44.1 kHz clips with random-fragment masks
 (generate_part1_data.create_random_mask semantics), n_fft 1024 / hop 256, K = 64, seed 42, 200 CD iterations,
 tol 1e-4; 512 clips per GPU, so 8 GPUs process the named 4096 clips (weak scaling: clips are independent, no
 data-path collective).  One step = the whole path (STFT -> frame mask -> imputation -> NMF fit -> recombine ->
 iSTFT) over the batch.  `value` is measured with the batch resident in HBM; `e2e` goes through the C ABI's
 host-buffer entry point (pinned host -> device -> host inside the timed region).
+
+The same JSON line carries, as objects next to the headline keys (--legs, default all):
+  "c5"            BASELINE configs[4] at EVERY N: the 1-hour signal, K = 128, 2048/512 -- one GPU at N = 1, time-frame-
+                  sharded H + all-reduce of the W partial sums at N > 1 (strong scaling); with its own e2e, roofline, parity
+                  against the oracle on a prefix and (N = 1) a same-box CPU figure;
+  "c4_full_4096"  (N = 1) all 4096 clips of configs[3] on one GPU through ainmf_inpaint_host (chunked by free memory);
+  "latency_cases" (N = 1) configs[0], [1], [2]: main4_NMF.py's 50 chained refits on the real segment, one 10 s clip with a
+                  2 s gap at 2048/512, one clip with the random-fragment mask; each with the CPU path beside it.
+`--impl reference` times the reference's own CPU path (scipy + sklearn through oracle/libcalls.py) for the same workloads.
 One JSON line is printed by rank 0.
 """
 from __future__ import annotations
@@ -34,7 +43,11 @@ WORKLOADS = {
                desc="BASELINE configs[3]: 10 s 44.1 kHz clips, random-fragment masks, K=64, 200 CD iterations"),
     "c2": dict(N=441000, n_fft=2048, hop=512, K=40, thr=1e-4, num=9, den=10, frac=0.9, seed=42, clips=1,
                desc="BASELINE configs[1]: one 10 s clip with a 2 s gap, n_fft 2048 / hop 512, K=40 (latency case)"),
+    "c3": dict(N=441000, n_fft=1024, hop=256, K=40, thr=0.01, num=4, den=5, frac=0.8, seed=42, clips=1,
+               desc="BASELINE configs[2]: one 10 s clip with the random-fragment mask of generate_part1_data, n_fft 1024 / hop 256, "
+                    "K=40 (latency case)"),
 }
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def peaks():
@@ -190,34 +203,21 @@ def use_all_host_threads():
         return int(os.environ.get("OMP_NUM_THREADS", cores))
 
 
-def run_reference(args, wl, rank):
-    if rank != 0:
-        return
-    cores = use_all_host_threads()
-    clips_per_step = 2 if wl["clips"] > 1 else 1
-    for _ in range(args.warmup):
-        cpu_leg(wl, 1)
-    t = 0.0
-    its = 0
-    for s in range(args.steps):
-        dt, it, _ = cpu_leg(wl, clips_per_step, first_clip=s * clips_per_step)
-        t += dt
-        its += it
-    audio_s = args.steps * clips_per_step * wl["N"] / SR
-    val = audio_s / t
-    line = {
-        "impl": "reference", "metric": "audio_seconds_restored_per_second", "value": val, "unit": "audio-s/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "n_fft": wl["n_fft"], "hop": wl["hop"], "rank": wl["K"],
-                   "max_iter": 200, "tol": 1e-4, "clips_per_step": clips_per_step},
-        "nmf_iters_per_s": its / t,
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{clips_per_step} clip(s) of the workload per step through scipy.signal.stft/istft + "
-                                   f"sklearn NMF(cd) (oracle/libcalls.py), OpenBLAS on {cores} threads, sweep single-threaded"},
-        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
+def newest_traffic(workload):
+    """ncu dram bytes per launch (profiles/*_traffic.json written by profiles/summarize.py), newest capture for this
+    workload; None when no capture of the current kernels has been committed."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for fn in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if fn.endswith("_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(pdir, fn)))
+            except Exception:
+                continue
+            if tj.get("workload", "c4") == workload:
+                tj["file"] = fn
+                best = tj
+    return best
 
 
 C5 = dict(N=158760000, n_fft=2048, hop=512, K=128, thr=1e-4, num=9, den=10, frac=0.9, seed=0,
@@ -225,8 +225,27 @@ C5 = dict(N=158760000, n_fft=2048, hop=512, K=128, thr=1e-4, num=9, den=10, frac
                "200 CD iterations; N>1: time-frame-sharded H + all-reduce of the W partial sums (strong scaling)")
 
 
-def c5_signal_device(device, N):
+def c5_signal_host(N):
     """0.1*N(0,1) + a bed of 8 sinusoids, zeroed on [s, s+2) s for s = 15, 45, ..., peak-normalised."""
+    rng = np.random.default_rng(0)
+    x = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    rs = np.random.RandomState(7)
+    fr, am = rs.uniform(100.0, 8000.0, 8), rs.uniform(0.05, 0.3, 8)
+    chunk = 1 << 22
+    for a in range(0, N, chunk):
+        b = min(N, a + chunk)
+        t = np.arange(a, b, dtype=np.float64) / SR
+        for j in range(8):
+            x[a:b] += (am[j] * np.sin(2 * np.pi * fr[j] * t)).astype(np.float32)
+    s = 15
+    while (s + 2) * SR <= N:
+        x[s * SR:(s + 2) * SR] = 0
+        s += 30
+    return x / np.abs(x).max()
+
+
+def c5_signal_device(device, N):
+    """The same family generated on the device (the 1-hour signal is 635 MB; parity is checked on a host-generated prefix)."""
     import torch
     g = torch.Generator(device=device).manual_seed(0)
     x = 0.1 * torch.randn(N, device=device, generator=g)
@@ -245,27 +264,333 @@ def c5_signal_device(device, N):
     return x / x.abs().max()
 
 
-def run_c5(args, rank, local_rank, world):
-    """The 1-hour signal (BASELINE configs[4]).  N=1: torch.ops.ainmf.nmf_inpaint; N>1: TimeShardedInpainter."""
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    import ainmf
-    from ainmf import _capi
-    L = ainmf._lib.lib()
-    h = ainmf._lib.handle(local_rank)
+def c5_cpu_sample(seconds=240.0, iters=6):
+    """BASELINE.md section 3 for configs[4], bounded: the reference's calls on a `seconds`-long prefix of the signal with
+    `iters` CD iterations; the once-per-signal stages and the per-iteration cost both scale linearly with the length, so
+    the hour costs (outside + per_iter * 200) * 3600 / seconds.  Returns (audio-s/s for the full config, detail dict)."""
+    from oracle import libcalls
+    from scipy import signal
+    N = int(seconds * SR)
+    x = c5_signal_host(N)
+    t0 = time.perf_counter()
+    Z, mag, phase, _ = libcalls.stft_mag_phase(x, SR, C5["n_fft"], C5["hop"])
+    bad = libcalls.column_mask(x, mag.shape[1], C5["hop"], C5["thr"], C5["frac"])
+    cur = libcalls.impute(mag, bad)
+    t1 = time.perf_counter()
+    W, H, n_iter, err = libcalls.nmf_fit(cur, C5["K"], C5["seed"], iters, 1e-4)
+    t2 = time.perf_counter()
+    final = mag.copy()
+    final[:, bad] = (W @ H)[:, bad]
+    Zr = final * np.exp(1j * phase)
+    _, y = signal.istft(Zr, SR, nperseg=C5["n_fft"], noverlap=C5["n_fft"] - C5["hop"])
+    t3 = time.perf_counter()
+    outside, per_iter = (t1 - t0) + (t3 - t2), (t2 - t1) / max(n_iter, 1)
+    full_s = (outside + per_iter * 200) * (C5["N"] / SR) / seconds
+    return (C5["N"] / SR) / full_s, dict(prefix_seconds=seconds, iterations_timed=n_iter, outside_loop_s=outside,
+                                         s_per_iteration=per_iter, extrapolated_seconds_for_the_hour=full_s,
+                                         cpu_seconds_spent=t3 - t0)
+
+
+class Ctx:
+    """Process-wide state of one rank."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: ainmf has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        import ainmf
+        from ainmf import _capi
+        self.ainmf, self.capi, self.ops = ainmf, _capi, ainmf.ops
+        self.L = ainmf._lib.lib()
+        self.h = ainmf._lib.handle(self.local_rank)
+        self.args = args
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.device, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def free(self):
+        self.ops._workspaces.clear()
+        self.torch.cuda.empty_cache()
+
+    def profile_iteration(self, step):
+        """Live CUDA-event time of the iteration's kernels during one extra step (outside the timed legs)."""
+        self.L.ainmf_profile(self.h, 1, None, None)
+        step()
+        self.torch.cuda.synchronize()
+        pms, pcn = (C.c_double * 6)(), (C.c_int64 * 6)()
+        self.L.ainmf_profile(self.h, 0, pms, pcn)
+        names = ["gram_Ht", "xht_gram_tc", "w_side_fused", "gram_W", "h_step_tc", "stop_rule"]
+        return {k: float(pms[i]) for i, k in enumerate(names)}, max(int(pcn[4]), 1)
+
+
+KERNEL_NAMES = {"h_step_tc": "h_step_ts_kernel (X^T.W contraction on tcgen05 + H coordinate sweep, one launch per iteration)",
+                "xht_gram_tc": "xht_ts_kernel (X.Ht contraction + Gram of Ht on tcgen05, one launch per iteration)",
+                "w_side_fused": "w_side_kernel (W sweep, W^T W and the H step's operands)"}
+NCU_NAMES = {"h_step_tc": "h_step_ts_kernel", "xht_gram_tc": "xht_ts_kernel", "w_side_fused": "w_side_kernel"}
+
+
+def roofline_object(kern_ms, n_it, F, T, K, units, workload, note_iteration):
+    """The contract's roofline object for the dominant kernel + the same accounting per kernel and for the whole iteration.
+    units = spectrograms one launch processes (clips; 1 for the long signal, whose T is this rank's slice)."""
+    peak, peak_src = peaks()
+    kb = {"gram_Ht": 4.0 * T * K + 4.0 * K * K, "xht_gram_tc": 4.0 * F * T + 4.0 * T * K + 4.0 * F * K,
+          "w_side_fused": 12.0 * F * K + 8.0 * K * K, "gram_W": 4.0 * F * K + 4.0 * K * K,
+          "h_step_tc": 4.0 * F * T + 4.0 * F * K + 8.0 * T * K + 4.0 * K * K, "stop_rule": 0.0}
+    tot = max(sum(kern_ms.values()), 1e-12)
+    kernels = {k: {"ms_per_launch": v / n_it, "share": v / tot,
+                   "hbm_frac": (kb[k] * units / (v / n_it * 1e-3) / 1e9 / peak) if v > 0 else None} for k, v in kern_ms.items()}
+    dom = max(kern_ms, key=lambda k: kern_ms[k])
+    dom_ms = kern_ms[dom] / n_it
+    dom_ach = kb[dom] * units / (dom_ms * 1e-3) / 1e9
+    iter_ms = tot / n_it
+    bytes_iter = alg_bytes_per_iter(F, T, K) * units
+    ach = bytes_iter / (iter_ms * 1e-3) / 1e9
+    traffic, tfile = None, None
+    tj = newest_traffic(workload)
+    if tj and NCU_NAMES.get(dom) in tj.get("dram_bytes_per_launch", {}):
+        n_units = tj.get("units") or tj.get("clips")
+        traffic = tj["dram_bytes_per_launch"][NCU_NAMES[dom]] / n_units * units if n_units else None
+        tfile = tj["file"]
+    return {"bound": "hbm", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": dom_ach, "peak": peak, "unit": "GB/s",
+            "frac": dom_ach / peak, "traffic": traffic, "traffic_source": tfile, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": kb[dom] * units, "ms_per_launch": dom_ms,
+            "iteration": {"kernel": note_iteration, "achieved": ach, "frac": ach / peak,
+                          "algorithmic_bytes_per_iteration": bytes_iter, "ms_per_iteration": iter_ms},
+            "kernels": kernels}
+
+
+def parity_vs_oracle(ctx, x_host, wl, K, max_iter=200):
+    """One host signal through the op and through the oracle: the gates of north_star as numbers."""
+    from oracle import libcalls
+    torch = ctx.torch
+    yo, st = libcalls.restore_columns(x_host, SR, n_fft=wl["n_fft"], hop=wl["hop"], threshold=wl["thr"], frac=wl["frac"], K=K,
+                                      seed=wl["seed"], max_iter=max_iter, return_all=True)
+    yg, ig, ng, _, _, eg, itg = ctx.ops.nmf_inpaint(torch.from_numpy(x_host[None]).to(ctx.device), wl["n_fft"], wl["hop"], K, max_iter,
+                                                    1e-4, wl["seed"], wl["thr"], wl["num"], wl["den"], -1, -1, 1, None, None)
+    bad, n = st["bad"], int(ng[0])
+    y = yg[0].cpu().numpy()
+    m = np.zeros(len(x_host), bool)
+    for c in bad:
+        m[max(0, c * wl["hop"] - wl["n_fft"] // 2):min(len(x_host), c * wl["hop"] + wl["n_fft"] // 2)] = True
+    return {"mask_bit_exact": bool(n == len(bad) and np.array_equal(ig[0, :n].cpu().numpy(), bad)),
+            "objective_rel_diff": abs(float(eg[0]) - st["err"]) / st["err"],
+            "snr_vs_oracle_db": float(libcalls.snr_db(yo, y)), "snr_restored_samples_db": float(libcalls.snr_db(yo[m], y[m])),
+            "n_iter": [int(itg[0]), st["n_iter"]], "max_iter": max_iter}
+
+
+# =====================================================================================================
+# clip batches (configs[3]; also the single-clip cases configs[1], configs[2])
+# =====================================================================================================
+def leg_clips(ctx, name, wl, steps, warmup, cpu_baseline=True, headline=False):
+    torch, L, h, ops = ctx.torch, ctx.L, ctx.h, ctx.ops
+    B, N, K = wl["clips"], wl["N"], wl["K"]
+    T, F, _ = ctx.capi.stft_geometry(L, N, wl["n_fft"], wl["hop"])
+    if B == 1:
+        x = torch.from_numpy(synth_host(wl, 0)[None]).to(ctx.device)        # the latency cases run the host-generated clip
+    else:
+        x = synth_device(wl, ctx.rank * B, B, ctx.device)
+    torch.cuda.synchronize()
+
+    def step():
+        return ops.nmf_inpaint(x, wl["n_fft"], wl["hop"], K, 200, 1e-4, wl["seed"], wl["thr"], wl["num"], wl["den"],
+                               -1, -1, 1, None, None)
+
+    t0 = time.perf_counter()
+    out = step()
+    torch.cuda.synchronize()
+    cold_ms = (time.perf_counter() - t0) * 1e3          # first call: seeded N(0,1) tables (host RNG), FFT tables, workspace
+    for _ in range(max(warmup - 1, 0)):
+        out = step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0 and headline:
+        sampler.start()
+    launches0 = L.ainmf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    ctx.barrier()
+    launches = L.ainmf_launch_count() - launches0
+    clocks = sampler.stop() if (ctx.rank == 0 and headline) else None
+    ms_total = ctx.max_over_ranks(e0.elapsed_time(e1))
+    y, idx, nb, Wf, Hf, err, nit = out
+    iters_done = int(nit.sum())
+    kern_ms, n_it = ctx.profile_iteration(step)
+    roofline = roofline_object(kern_ms, n_it, F, T, K, B, name,
+                               "whole CD iteration = xht_ts_kernel + reduce_splits + w_side_kernel + w_finish_kernel + h_step_ts_kernel + stop_kernel")
+
+    # ---- end-to-end leg through the C ABI with HOST buffers -----------------------------------------
+    xh = torch.empty((B, N), dtype=torch.float32).pin_memory()
+    xh.copy_(x)
+    yh = torch.empty((B, N), dtype=torch.float32).pin_memory()
+    nbh = np.zeros(B, np.int32); errh = np.zeros(B, np.float32); nih = np.zeros(B, np.int32)
+    p = ctx.capi.default_params(L, batch=B, n_samples=N, n_fft=wl["n_fft"], hop=wl["hop"], rank=K, max_iter=200, tol=1e-4,
+                                seed=wl["seed"], threshold=wl["thr"], frac_num=wl["num"], frac_den=wl["den"])
+    del out, y, idx, Wf, Hf
+    ctx.free()
+
+    def e2e_step():
+        rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()),
+                                  nbh.ctypes.data_as(C.c_void_p), errh.ctypes.data_as(C.c_void_p),
+                                  nih.ctypes.data_as(C.c_void_p), 0)
+        ctx.ainmf._lib.check(rc, ctx.local_rank)
+
+    for _ in range(warmup):
+        e2e_step()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ctx.barrier()
+    audio_s_step = ctx.world * B * N / SR
+    line = {
+        "metric": "audio_seconds_restored_per_second", "value": audio_s_step * steps / (ms_total * 1e-3), "unit": "audio-s/s",
+        "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: {wl['desc']}", "clips_per_gpu": B, "n_samples": N, "n_fft": wl["n_fft"],
+                   "hop": wl["hop"], "F": F, "T": T, "rank": K, "max_iter": 200, "tol": 1e-4, "solver": "cd",
+                   "l2": ("inputs (%.0f MB/GPU of waveform, %.1f GB of spectrogram) exceed the 126 MB L2" % (B * N * 4 / 1e6, B * F * T * 4 / 1e9))
+                         if B > 64 else "latency case: one clip (%.1f MB of spectrogram) fits the L2 and stays there across the 200 iterations by design; "
+                                        "not a bandwidth figure" % (F * T * 4 / 1e6)},
+        "nmf_iters_per_s": ctx.world * B * 200 / (sum(kern_ms.values()) * 1e-3) if sum(kern_ms.values()) > 0 else None,
+        "nmf_iterations_done_last_step": iters_done,
+        "cold_first_call_ms": cold_ms,
+        "e2e": {"value": audio_s_step * steps / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": B * N * 4,
+                "d2h_bytes_per_step": B * N * 4 + B * 12, "ms_per_step": e2e_ms / steps,
+                "api": "ainmf_inpaint_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None, "parity": None,
+    }
+    if ctx.rank == 0 and ctx.world == 1 and cpu_baseline:
+        n_cpu = 8 if B > 1 else 1
+        cores = use_all_host_threads()
+        dt, its, outs = cpu_leg(wl, n_cpu)
+        line["cpu_baseline"] = {"value": n_cpu * N / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_cpu} clip(s) of the workload, serially, through scipy.signal.stft/istft + sklearn NMF(cd) "
+                                          f"(oracle/libcalls.py); OpenBLAS threads = {cores}, coordinate sweep single-threaded",
+                                "nmf_iters_per_s": its / dt, "seconds": dt}
+        line["parity"] = [parity_vs_oracle(ctx, o[0], wl, K) for o in outs[:2]]
+    del xh, yh
+    ctx.free()
+    return line
+
+
+def leg_c4_full(ctx, steps=1):
+    """All 4096 clips of configs[3] on ONE GPU: host buffers, chunked by the library (strong-scaling point of the c4 curve)."""
+    torch, L, h = ctx.torch, ctx.L, ctx.h
+    wl = dict(WORKLOADS["c4"])
+    Btot, N, K = 4096, wl["N"], wl["K"]
+    try:
+        xh = torch.empty((Btot, N), dtype=torch.float32).pin_memory()
+        yh = torch.empty((Btot, N), dtype=torch.float32).pin_memory()
+    except Exception as e:                                   # host without 14.5 GB of pinnable memory
+        return {"unavailable": f"cannot pin 2 x {Btot * N * 4 / 1e9:.1f} GB of host memory: {e}"}
+    for b0 in range(0, Btot, 512):
+        xh[b0:b0 + 512].copy_(synth_device(wl, b0, 512, ctx.device))
+    torch.cuda.synchronize()
+    ctx.free()
+    nbh = np.zeros(Btot, np.int32); errh = np.zeros(Btot, np.float32); nih = np.zeros(Btot, np.int32)
+    p = ctx.capi.default_params(L, batch=Btot, n_samples=N, n_fft=wl["n_fft"], hop=wl["hop"], rank=K, max_iter=200, tol=1e-4,
+                                seed=wl["seed"], threshold=wl["thr"], frac_num=wl["num"], frac_den=wl["den"])
+
+    def call():
+        rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), nbh.ctypes.data_as(C.c_void_p),
+                                  errh.ctypes.data_as(C.c_void_p), nih.ctypes.data_as(C.c_void_p), 0)
+        ctx.ainmf._lib.check(rc, ctx.local_rank)
+
+    call()                                                   # warm (workspace, pinned staging)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    out = {"clips": Btot, "api": "ainmf_inpaint_host (host buffers, chunked by free device memory)", "seconds_per_call": dt,
+           "value": Btot * N / SR / dt, "unit": "audio-s/s", "h2d_bytes": Btot * N * 4, "d2h_bytes": Btot * N * 4,
+           "nmf_iterations_done": int(nih.sum()), "clips_with_bad_frames": int((nbh > 0).sum())}
+    del xh, yh
+    ctx.free()
+    return out
+
+
+# =====================================================================================================
+# configs[0]: main4_NMF.py on the real 50 ms segment (the shipped golden fixture): 50 chained refits with early stop
+# =====================================================================================================
+def leg_c1(ctx, steps=5, cpu_baseline=True):
+    torch = ctx.torch
+    g = np.load(os.path.join(GOLDEN, "c1_part0.npz"))
+    ainmf = ctx.ainmf
+    lab = ainmf.SpectralInpainter.__new__(ainmf.SpectralInpainter)
+    ainmf.SpectralInpainter.__init__(lab, filename=None, duration=0.05, device=str(ctx.device))
+    lab.sr = int(g["sr"])
+    lab.raw_audio = g["raw"].copy()
+    lab.apply_mask(0.2)
+    launches0 = ctx.L.ainmf_launch_count()
+    lab.restore_with_nmf(n_components=40, n_iter=50)
+    launches = ctx.L.ainmf_launch_count() - launches0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = lab.restore_with_nmf(n_components=40, n_iter=50)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    dur = len(lab.raw_audio) / lab.sr
+    res = {"workload": "c1: BASELINE configs[0]: main4_NMF.py on the 50 ms real segment (257 x 19, K=40, 50 refits with early stop), "
+                       "through ainmf.SpectralInpainter.restore_with_nmf (host arrays in and out)",
+           "seconds_per_call": dt, "value": dur / dt, "unit": "audio-s/s", "n_iter_last_refit": lab.n_iter_,
+           "launches_per_call": int(launches), "data": "tests/golden/c1_part0.npz (the reference's own segment)"}
+    if cpu_baseline:
+        from oracle import libcalls
+        cores = use_all_host_threads()
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            yo, st = libcalls.part0_restore(g["raw"], lab.corrupted_audio, lab.sr, lab.gap_start, lab.gap_end, return_all=True)
+            best = min(best, time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": dur / best, "unit": "audio-s/s", "cores": cores, "kind": "port", "seconds": best,
+                               "sample": "the whole config (best of 3) through oracle/libcalls.part0_restore"}
+        res["parity"] = {"snr_vs_oracle_db": float(libcalls.snr_db(yo, out)), "n_iter_last_refit": [lab.n_iter_, st["n_iters"][-1]],
+                         "objective_rel_diff": abs(lab.reconstruction_err_ - st["err"]) / st["err"]}
+        res["speedup_vs_cpu"] = best / dt
+    return res
+
+
+# =====================================================================================================
+# configs[4]: the 1-hour signal
+# =====================================================================================================
+def leg_c5(ctx, steps, warmup, seconds=0.0, cpu_baseline=True, clocks=False):
+    """N=1: torch.ops.ainmf.nmf_inpaint; N>1: TimeShardedInpainter (time-frame split + all-reduce of the W partial sums)."""
+    torch, L, h = ctx.torch, ctx.L, ctx.h
     wl = dict(C5)
-    if args.seconds > 0:
-        wl["N"] = int(args.seconds * SR)
-    N, K = wl["N"], wl["K"]
-    T, F, _ = _capi.stft_geometry(L, N, wl["n_fft"], wl["hop"])
-    x = c5_signal_device(device, N)
+    if seconds > 0:
+        wl["N"] = int(seconds * SR)
+    N, K, world = wl["N"], wl["K"], ctx.world
+    T, F, _ = ctx.capi.stft_geometry(L, N, wl["n_fft"], wl["hop"])
+    x = c5_signal_device(ctx.device, N)
     if world > 1:
         from ainmf.sharding import TimeShardedInpainter
-        tsi = TimeShardedInpainter(device)
+        tsi = TimeShardedInpainter(ctx.device)
         pl = tsi.plan(N, wl["n_fft"], wl["hop"])
         xl = x[pl["x_begin"]:pl["x_end"]].clone()
         del x
@@ -274,50 +599,39 @@ def run_c5(args, rank, local_rank, world):
         def step():
             return tsi.restore(xl, N, n_fft=wl["n_fft"], hop=wl["hop"], rank=K, max_iter=200, tol=1e-4, seed=wl["seed"],
                                threshold=wl["thr"], frac=(wl["num"], wl["den"]))
+        src = xl
     else:
         xb = x[None]
 
         def step():
-            out = ainmf.ops.nmf_inpaint(xb, wl["n_fft"], wl["hop"], K, 200, 1e-4, wl["seed"], wl["thr"], wl["num"], wl["den"],
-                                        -1, -1, 1, None, None)
+            out = ctx.ops.nmf_inpaint(xb, wl["n_fft"], wl["hop"], K, 200, 1e-4, wl["seed"], wl["thr"], wl["num"], wl["den"],
+                                      -1, -1, 1, None, None)
             return out[0][0], dict(n_bad=out[2], n_iter=out[6], err=out[5])
+        src = x
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    t0 = time.perf_counter()
+    y, info = step()
+    torch.cuda.synchronize()
+    cold_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(max(warmup - 1, 0)):
         y, info = step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0 and clocks:
         sampler.start()
     launches0 = L.ainmf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         y, info = step()
     e1.record()
-    barrier()
+    ctx.barrier()
     launches = L.ainmf_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    # kernel-level timing
-    L.ainmf_profile(h, 1, None, None)
-    step()
-    torch.cuda.synchronize()
-    pms, pcn = (C.c_double * 6)(), (C.c_int64 * 6)()
-    L.ainmf_profile(h, 0, pms, pcn)
-    names = ["gram_Ht", "xht_gram_tc", "w_side_fused", "gram_W", "h_step_tc", "stop_rule"]
-    kern_ms = {k: float(pms[i]) for i, k in enumerate(names)}
-    n_it = max(int(pcn[4]), 1)
-    iter_ms = sum(kern_ms.values()) / n_it          # this rank's kernels; the all-reduce sits between them
+    clk = sampler.stop() if (ctx.rank == 0 and clocks) else None
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    kern_ms, n_it = ctx.profile_iteration(step)
+    kernels_per_step = ctx.max_over_ranks(sum(kern_ms.values()))
     # end to end: pinned host -> device -> host around the same call
-    src = xl if world > 1 else x
     xh = torch.empty(src.shape, dtype=torch.float32).pin_memory()
     xh.copy_(src)
     yh = torch.empty(y.shape, dtype=torch.float32).pin_memory()
@@ -328,50 +642,125 @@ def run_c5(args, rank, local_rank, world):
         yh.copy_(yy, non_blocking=True)
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         e2e_step()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    barrier()
-    if rank == 0:
-        peak, peak_src = peaks()
-        Tl = T // world
-        bytes_iter = alg_bytes_per_iter(F, Tl, K)        # per GPU: its slice of V and Ht, replicated W
-        achieved = bytes_iter / (iter_ms * 1e-3) / 1e9
-        h_bytes = 4.0 * F * Tl + 4.0 * F * K + 8.0 * Tl * K + 4.0 * K * K
-        audio_s = N / SR
-        line = {
-            "metric": "audio_seconds_restored_per_second", "value": audio_s * args.steps / (float(ms[0]) * 1e-3),
-            "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(ms[0]) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c5: " + wl["desc"], "n_samples": N, "n_fft": wl["n_fft"], "hop": wl["hop"], "F": F, "T": T,
-                       "rank": K, "max_iter": 200, "tol": 1e-4, "solver": "cd",
-                       "l2": "the spectrogram slice per GPU (%.2f GB) exceeds the 126 MB L2" % (F * Tl * 4 / 1e9)},
-            "nmf_iters_per_s": 200 * args.steps / (float(ms[0]) * 1e-3),
-            "n_iter": int(info["n_iter"][0]), "n_bad": int(info["n_bad"][0]), "objective": float(info["err"][0]),
-            "e2e": {"value": audio_s * args.steps / (float(e2e_ms[0]) * 1e-3), "unit": "audio-s/s",
-                    "h2d_bytes_per_step": int(src.numel() * 4), "d2h_bytes_per_step": int(y.numel() * 4),
-                    "ms_per_step": float(e2e_ms[0]) / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "h_step_ts_kernel on this rank's frame slice (X^T.W contraction on tcgen05 + H coordinate sweep)",
-                         "achieved": h_bytes / (kern_ms["h_step_tc"] / n_it * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": h_bytes / (kern_ms["h_step_tc"] / n_it * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": h_bytes, "ms_per_launch": kern_ms["h_step_tc"] / n_it,
-                         "iteration": {"kernel": "whole CD iteration on this rank (the W side is replicated, not sharded)",
-                                       "achieved": achieved, "frac": achieved / peak,
-                                       "algorithmic_bytes_per_iteration": bytes_iter, "ms_per_iteration": iter_ms},
-                         "kernels_ms_per_launch": {k: v / n_it for k, v in kern_ms.items()}},
-            "cpu_baseline": None,
-        }
+    e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ctx.barrier()
+    Tl = T // world
+    audio_s = N / SR
+    step_ms = ms / steps
+    res = {
+        "metric": "audio_seconds_restored_per_second", "value": audio_s * steps / (ms * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "n_ranks": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c5: " + wl["desc"], "n_samples": N, "n_fft": wl["n_fft"], "hop": wl["hop"], "F": F, "T": T,
+                   "frames_per_rank": Tl, "rank": K, "max_iter": 200, "tol": 1e-4, "solver": "cd",
+                   "l2": "the spectrogram slice per GPU (%.2f GB) exceeds the 126 MB L2" % (F * Tl * 4 / 1e9)},
+        "nmf_iters_per_s": 200 * steps / (ms * 1e-3),
+        "n_iter": int(info["n_iter"][0]), "n_bad": int(info["n_bad"][0]), "objective": float(info["err"][0]),
+        "cold_first_call_ms": cold_ms,
+        "ms_per_iteration_kernels": kernels_per_step / n_it,
+        "ms_per_step_outside_iteration_kernels": step_ms - kernels_per_step,
+        "exposed_note": "ms_per_step minus the CUDA-event time of the iteration's kernels (max over ranks): STFT, mask, imputation, "
+                        "initial factors, objective, iSTFT, launch gaps and, at N > 1, the all-reduces between the kernels",
+        "e2e": {"value": audio_s * steps / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(src.numel() * 4),
+                "d2h_bytes_per_step": int(y.numel() * 4), "ms_per_step": e2e_ms / steps},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": roofline_object(kern_ms, n_it, F, Tl, K, 1, "c5",
+                                    "whole CD iteration on this rank (its frame slice; the W side is replicated, not sharded)"),
+        "cpu_baseline": None, "parity": None,
+    }
+    del xh, yh, y, src
+    if world == 1:
+        del xb, x
+    ctx.free()
+    if ctx.rank == 0 and world == 1 and cpu_baseline:
+        cores = use_all_host_threads()
+        val, det = c5_cpu_sample()
+        res["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                               "sample": "a %.0f s prefix of the signal: STFT, mask, imputation, recombination and iSTFT once + %d CD "
+                                         "iterations through scipy + sklearn (oracle/libcalls.py), extrapolated linearly to the hour at 200 "
+                                         "iterations (BASELINE.md section 3); OpenBLAS threads = %d" % (det["prefix_seconds"], det["iterations_timed"], cores),
+                               **det}
+        res["parity"] = parity_vs_oracle(ctx, c5_signal_host(int(60 * SR)), wl, K, max_iter=30)
+        res["parity"]["note"] = "60 s prefix, 30 iterations (a full-length oracle run takes ~20 min of CPU)"
+        ctx.free()
+    return res
+
+
+# =====================================================================================================
+# reference arm: the reference's own CPU path (scipy + sklearn via oracle/libcalls.py), rank 0 only
+# =====================================================================================================
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = use_all_host_threads()
+    name = args.workload
+    base = {"impl": "reference", "metric": "audio_seconds_restored_per_second", "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+    if name == "c5":
+        val, det, t = 0.0, None, 0.0
+        for _ in range(max(args.steps, 1)):
+            v, det = c5_cpu_sample(seconds=120.0, iters=6)
+            val += v
+            t += det["cpu_seconds_spent"]
+        val /= max(args.steps, 1)
+        line = dict(base, value=val, ms_per_step=1e3 * t / max(args.steps, 1), scaling="strong",
+                    config={"workload": "c5: " + C5["desc"], "n_fft": C5["n_fft"], "hop": C5["hop"], "rank": C5["K"], "max_iter": 200, "tol": 1e-4},
+                    cpu_baseline={"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                  "sample": "per step: a 120 s prefix, every stage once + 6 CD iterations, extrapolated to the hour at 200 iterations", **det},
+                    e2e={"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return
+    if name == "c1":
+        class _NoGpu:
+            pass
+        from oracle import libcalls
+        g = np.load(os.path.join(GOLDEN, "c1_part0.npz"))
+        cor, gs, ge = libcalls.part0_apply_mask(g["raw"])
+        t = 0.0
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            libcalls.part0_restore(g["raw"], cor, int(g["sr"]), gs, ge)
+            if i >= args.warmup:
+                t += time.perf_counter() - t0
+        dur = len(g["raw"]) / int(g["sr"])
+        val = dur * args.steps / t
+        line = dict(base, value=val, ms_per_step=1e3 * t / args.steps, scaling="weak", data="tests/golden/c1_part0.npz",
+                    config={"workload": "c1: BASELINE configs[0]: main4_NMF.py on the 50 ms real segment"},
+                    cpu_baseline={"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": "the whole config per step"},
+                    e2e={"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    wl = dict(WORKLOADS[name])
+    clips_per_step = 2 if wl["clips"] > 1 else 1
+    for _ in range(args.warmup):
+        cpu_leg(wl, 1)
+    t, its = 0.0, 0
+    for s in range(args.steps):
+        dt, it, _ = cpu_leg(wl, clips_per_step, first_clip=s * clips_per_step)
+        t += dt
+        its += it
+    audio_s = args.steps * clips_per_step * wl["N"] / SR
+    val = audio_s / t
+    line = dict(base, value=val, ms_per_step=1e3 * t / args.steps, scaling="weak",
+                config={"workload": f"{name}: {wl['desc']}", "n_fft": wl["n_fft"], "hop": wl["hop"], "rank": wl["K"],
+                        "max_iter": 200, "tol": 1e-4, "clips_per_step": clips_per_step},
+                nmf_iters_per_s=its / t,
+                cpu_baseline={"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                              "sample": f"{clips_per_step} clip(s) of the workload per step through scipy.signal.stft/istft + "
+                                        f"sklearn NMF(cd) (oracle/libcalls.py), OpenBLAS on {cores} threads, sweep single-threaded"},
+                e2e={"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    if name == "c4" and "c5" in args.legs:
+        v5, det = c5_cpu_sample(seconds=120.0, iters=6)
+        line["c5"] = {"impl": "reference", "value": v5, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                      "sample": "a 120 s prefix, every stage once + 6 CD iterations, extrapolated to the hour at 200 iterations", **det}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -381,211 +770,51 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--legs", default="c5,c4_full,latency", help="extra objects of the default (c4) line: comma list of c5, c4_full, "
+                                                                 "latency; 'none' for the headline only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload == "c5":
-        if args.warmup < 3:
-            args.warmup = 3
-        if args.impl == "reference":
-            raise SystemExit("--impl reference supports the clip workloads (c4, c2)")
-        return run_c5(args, int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
-                      int(os.environ.get("WORLD_SIZE", "1")))
-    wl = dict(WORKLOADS[args.workload])
-    if args.clips > 0:
-        wl["clips"] = args.clips
+    args.legs = [] if args.legs == "none" else [s for s in args.legs.split(",") if s]
     if args.warmup < 3:
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, rank)
         return
-
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: ainmf has no CPU path")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    import ainmf
-    from ainmf import _capi
-    ops = ainmf.ops
-    L = ainmf._lib.lib()
-    h = ainmf._lib.handle(local_rank)
-
-    B, N = wl["clips"], wl["N"]
-    T, F, _ = _capi.stft_geometry(L, N, wl["n_fft"], wl["hop"])
-    K = wl["K"]
-    x = synth_device(wl, rank * B, B, device)
-    torch.cuda.synchronize()
-
-    def step():
-        return ops.nmf_inpaint(x, wl["n_fft"], wl["hop"], K, 200, 1e-4, wl["seed"], wl["thr"], wl["num"], wl["den"],
-                               -1, -1, 1, None, None)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident leg (`value`) -------------------------------------------------------------
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = L.ainmf_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    launches = L.ainmf_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms[0])
-    y, idx, nb, Wf, Hf, err, nit = out
-    iters_done = int(nit.sum())
-
-    # ---- kernel-level timing of the NMF iteration (CUDA events on the launching stream, outside the timed legs) ----
-    L.ainmf_profile(h, 1, None, None)
-    step()
-    torch.cuda.synchronize()
-    pms = (C.c_double * 6)()
-    pcn = (C.c_int64 * 6)()
-    L.ainmf_profile(h, 0, pms, pcn)
-    kern_names = ["gram_Ht", "xht_gram_tc", "w_side_fused", "gram_W", "h_step_tc", "stop_rule"]
-    kern_ms = {k: float(pms[i]) for i, k in enumerate(kern_names)}
-    n_it = max(int(pcn[4]), 1)
-    iter_ms = sum(kern_ms.values()) / n_it
-    peak, peak_src = peaks()
-    bytes_iter = alg_bytes_per_iter(F, T, K) * B
-    achieved = bytes_iter / (iter_ms * 1e-3) / 1e9
-    # per-kernel algorithmic bytes (float32): what each launch must move at least
-    # (gram_Ht / gram_W are separate launches only on the FFMA path, K < 64: on the tensor-core path the Gram of Ht comes
-    # out of the X.Ht kernel and W^T W out of the fused W-side kernel, so their entries read 0)
-    kb = {"gram_Ht": 4.0 * T * K + 4.0 * K * K, "xht_gram_tc": 4.0 * F * T + 4.0 * T * K + 4.0 * F * K,
-          "w_side_fused": 12.0 * F * K + 8.0 * K * K, "gram_W": 4.0 * F * K + 4.0 * K * K,
-          "h_step_tc": 4.0 * F * T + 4.0 * F * K + 8.0 * T * K + 4.0 * K * K, "stop_rule": 0.0}
-    kernels = {k: {"ms_per_launch": kern_ms[k] / n_it, "share": kern_ms[k] / max(sum(kern_ms.values()), 1e-12),
-                   "hbm_frac": ((kb[k] * B / (kern_ms[k] / n_it * 1e-3) / 1e9) / peak) if kern_ms[k] > 0 else None}
-               for k in kern_names}
-
-    # roofline of the dominant kernel (the contract's object) + the same accounting for the whole iteration
-    dom = max(kern_names, key=lambda k: kern_ms[k])
-    dom_kernel = {"h_step_tc": "h_step_ts_kernel (X^T.W contraction on tcgen05 + H coordinate sweep, one launch per iteration)",
-                  "xht_gram_tc": "xht_ts_kernel (X.Ht contraction + Gram of Ht on tcgen05, one launch per iteration)",
-                  "w_side_fused": "w_side_kernel"}.get(dom, dom)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
-    if os.path.exists(tpath) and args.workload == "c4":
-        tj = json.load(open(tpath))
-        key = {"h_step_tc": "h_step_ts_kernel", "xht_gram_tc": "xht_ts_kernel", "w_side_fused": "w_side_kernel"}.get(dom)
-        if key in tj["dram_bytes_per_launch"]:
-            traffic = tj["dram_bytes_per_launch"][key] / tj["clips"] * B     # ncu dram read+write per launch, scaled to B clips
-    dom_ms = kern_ms[dom] / n_it
-    dom_achieved = kb[dom] * B / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
-                "frac": dom_achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": kb[dom] * B, "ms_per_launch": dom_ms,
-                "limiter": "tensor pipe: 2 tcgen05.mma per 8 contraction elements (tf32 main term + bf16 cross terms), ~277 cycles per 128 frames x 8 bins",
-                "iteration": {"kernel": "whole CD iteration = xht_ts_kernel + reduce_splits + w_side_kernel + w_finish_kernel + h_step_ts_kernel + stop_kernel",
-                              "achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_iteration": bytes_iter,
-                              "ms_per_iteration": iter_ms},
-                "kernels": kernels}
-
-    # ---- end-to-end leg through the C ABI with HOST buffers -----------------------------------------
-    xh = torch.empty((B, N), dtype=torch.float32).pin_memory()
-    xh.copy_(x)
-    yh = torch.empty((B, N), dtype=torch.float32).pin_memory()
-    nbh = np.zeros(B, np.int32); errh = np.zeros(B, np.float32); nih = np.zeros(B, np.int32)
-    p = _capi.default_params(L, batch=B, n_samples=N, n_fft=wl["n_fft"], hop=wl["hop"], rank=K, max_iter=200, tol=1e-4,
-                             seed=wl["seed"], threshold=wl["thr"], frac_num=wl["num"], frac_den=wl["den"])
-    del out, y, idx, Wf, Hf
-    ops._workspaces.clear()
-    torch.cuda.empty_cache()
-
-    def e2e_step():
-        rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()),
-                                  nbh.ctypes.data_as(C.c_void_p), errh.ctypes.data_as(C.c_void_p),
-                                  nih.ctypes.data_as(C.c_void_p), 0)
-        ainmf._lib.check(rc, local_rank)
-
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    barrier()
-    audio_s_step = world * B * N / SR
-    value = audio_s_step * args.steps / (ms_total * 1e-3)
-    e2e_value = audio_s_step * args.steps / (float(e2e_ms[0]) * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- parity spot check + CPU baseline (rank 0, N=1 only; bounded sample) -------------------------
-    parity, cpu = None, None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import libcalls
-        n_cpu = 8 if B > 1 else 1
-        cores = use_all_host_threads()
-        dt, its, outs = cpu_leg(wl, n_cpu)
-        cpu = {"value": n_cpu * N / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} clips of the workload, serially, through scipy.signal.stft/istft + sklearn NMF(cd) "
-                         f"(oracle/libcalls.py); OpenBLAS threads = {cores}, coordinate sweep single-threaded",
-               "nmf_iters_per_s": its / dt, "seconds": dt}
-        xs = np.stack([o[0] for o in outs[:2]])
-        yg, ig, ng, _, _, eg, itg = ops.nmf_inpaint(torch.from_numpy(xs).to(device), wl["n_fft"], wl["hop"], K, 200, 1e-4,
-                                                    wl["seed"], wl["thr"], wl["num"], wl["den"], -1, -1, 1, None, None)
-        parity = []
-        for i in range(xs.shape[0]):
-            _, yo, st = outs[i]
-            bad = st["bad"]
-            n = int(ng[i])
-            parity.append({"mask_bit_exact": bool(n == len(bad) and np.array_equal(ig[i, :n].cpu().numpy(), bad)),
-                           "objective_rel_diff": abs(float(eg[i]) - st["err"]) / st["err"],
-                           "snr_vs_oracle_db": float(libcalls.snr_db(yo, yg[i].cpu().numpy())),
-                           "n_iter": [int(itg[i]), st["n_iter"]]})
-
-    line = {
-        "metric": "audio_seconds_restored_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "clips_per_gpu": B, "n_samples": N, "n_fft": wl["n_fft"],
-                   "hop": wl["hop"], "F": F, "T": T, "rank": K, "max_iter": 200, "tol": 1e-4, "solver": "cd",
-                   "l2": "inputs (%.0f MB/GPU of waveform, %.1f GB of spectrogram) exceed the 126 MB L2" % (B * N * 4 / 1e6, B * F * T * 4 / 1e9)},
-        "nmf_iters_per_s": world * B * 200 / (sum(kern_ms.values()) * 1e-3) if sum(kern_ms.values()) > 0 else None,
-        "nmf_iterations_done_last_step": iters_done,
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * N * 4 + B * 12,
-                "ms_per_step": float(e2e_ms[0]) / args.steps, "api": "ainmf_inpaint_host (C ABI, pinned host buffers)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-        "parity": parity,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx = Ctx(args)
+    cpu = not args.no_cpu_baseline
+    if args.workload == "c5":
+        line = leg_c5(ctx, args.steps, args.warmup, args.seconds, cpu, clocks=True)
+    elif args.workload == "c1":
+        r = leg_c1(ctx, max(args.steps, 1), cpu)
+        line = {"metric": "audio_seconds_restored_per_second", "value": r["value"], "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_call"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": r["data"], "config": {"workload": r["workload"]},
+                "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 2205 * 4, "d2h_bytes_per_step": 2205 * 4},
+                "gpu_launches": r["launches_per_call"] * args.steps, "cpu_baseline": r.get("cpu_baseline"), "parity": r.get("parity")}
+    else:
+        wl = dict(WORKLOADS[args.workload])
+        if args.clips > 0:
+            wl["clips"] = args.clips
+        line = leg_clips(ctx, args.workload, wl, args.steps, args.warmup, cpu, headline=True)
+        if args.workload == "c4":
+            if "c5" in args.legs:
+                line["c5"] = leg_c5(ctx, min(args.steps, 3), 3, args.seconds, cpu)
+            if ctx.world == 1 and "c4_full" in args.legs:
+                line["c4_full_4096"] = leg_c4_full(ctx)
+            if ctx.world == 1 and "latency" in args.legs:
+                lat = {"c1": leg_c1(ctx, 3, cpu)}
+                for nm in ("c2", "c3"):
+                    r = leg_clips(ctx, nm, dict(WORKLOADS[nm]), 5, 3, cpu)
+                    lat[nm] = {k: r[k] for k in ("value", "unit", "ms_per_step", "config", "cold_first_call_ms", "e2e", "cpu_baseline", "parity", "nmf_iters_per_s")}
+                    lat[nm]["ms_per_iteration"] = r["roofline"]["iteration"]["ms_per_iteration"]
+                line["latency_cases"] = lat
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

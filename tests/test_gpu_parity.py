@@ -1,7 +1,7 @@
 """GPU parity tests: the CUDA path (through torch.ops.ainmf -> C ABI -> sm_100a kernels) against the oracle.
 
 Tolerances are north_star's: masks / indices bit-exact; |Z| rel-L2 <= 1e-5; objective rel <= 1e-4;
-restored-waveform SNR vs the reference output >= 60 dB (in-gap SNR is reported and gated at >= 40 dB, the
+restored-waveform SNR vs the reference output >= 60 dB (in-gap SNR is gated at >= 60 dB as well, the
 whole-wave figure being dominated by untouched frames).
 """
 import numpy as np
@@ -175,8 +175,8 @@ def test_nmf_fit_seeded_init_and_early_stop(ops):
     Wo, Ho, no, eo = libcalls.nmf_fit(X, K, seed=0, max_iter=200, tol=1e-4)
     W, H, err, nit = ops.nmf_fit(dev(X[None]), K, 200, 1e-4, 0, None, None)
     assert no < 200, "oracle should stop early on this matrix"
-    assert abs(int(nit[0]) - no) <= 2
-    assert abs(float(err[0]) - eo) <= 1e-3 * max(eo, 1e-6) + 1e-6
+    assert int(nit[0]) == no                                          # small problem: reference-order violation sum
+    assert abs(float(err[0]) - eo) <= 1e-4 * eo
     # one iteration from the seeded init must agree tightly
     Wo1, Ho1, _, _ = libcalls.nmf_fit(X, K, seed=0, max_iter=1, tol=0.0)
     W1, H1, _, _ = ops.nmf_fit(dev(X[None]), K, 1, 0.0, 0, None, None)
@@ -242,7 +242,7 @@ def test_c2_golden_end_to_end(ops, golden):
     yn = y[0].cpu().numpy()
     gs, ge = c2["gap"]
     assert libcalls.snr_db(yo, yn) >= 60.0                                         # north_star: >= 60 dB
-    assert libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 40.0
+    assert libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 60.0
     shipped = pcm.astype(np.int32) + c2["shipped_minus_input_i16"]
     q = ops.store_pcm16(y[0]).cpu().numpy().astype(np.int32)
     outside = np.ones(len(q), bool)
@@ -273,7 +273,7 @@ def test_c2_at_2048_512_vs_oracle(ops, golden):
     assert abs(float(err[0]) - st["err"]) <= 1e-4 * st["err"]
     gs, ge = golden.c2["gap"]
     yn = y[0].cpu().numpy()
-    assert libcalls.snr_db(yo, yn) >= 60.0 and libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 40.0
+    assert libcalls.snr_db(yo, yn) >= 60.0 and libcalls.snr_db(yo[gs:ge], yn[gs:ge]) >= 60.0
 
 
 def test_c1_part0_golden(ops, golden):
@@ -289,11 +289,15 @@ def test_c1_part0_golden(ops, golden):
     out = lab.restore_with_nmf(n_components=40, n_iter=50)
     assert lab.cols_ == tuple(c1["cols"]) == (6, 10)
     assert libcalls.snr_db(c1["restored"], out) >= 60.0
-    assert libcalls.snr_db(c1["restored"][gs:ge], out[gs:ge]) >= 40.0
+    assert libcalls.snr_db(c1["restored"][gs:ge], out[gs:ge]) >= 60.0
     q = libcalls.quantise_int16(out).astype(np.int32)
-    assert np.max(np.abs(q - c1["shipped_restored_i16"].astype(np.int32))) <= 3
-    assert abs(lab.n_iter_ - int(c1["n_iters"][-1])) <= 3
-    assert abs(lab.reconstruction_err_ - float(c1["err"])) <= 0.05 * float(c1["err"]) + 1e-6
+    assert np.max(np.abs(q - c1["shipped_restored_i16"].astype(np.int32))) <= 1       # the oracle itself is within 1 LSB
+    # the stop rule adds the violations in sklearn's order and precision where the decision is close (stop_kernel), so the
+    # 50 chained refits stop where the reference's did
+    assert lab.n_iter_ == int(c1["n_iters"][-1])
+    # the final residual is 1e-4 of ||X||: its float32 cancellation noise, eps.||X|| / err = 4e-4, is in the reference's own
+    # figure too, so the 1e-4 gate of the other configs (residual ~ 0.1 ||X||) is below what this number carries
+    assert abs(lab.reconstruction_err_ - float(c1["err"])) <= 5e-4 * float(c1["err"])
 
 
 # ---- edge cases --------------------------------------------------------------------------------------------
@@ -386,8 +390,32 @@ def test_invalid_arguments_raise(ops):
     with pytest.raises(ainmf.AinmfError) as e:
         _run_columns(ops, np.zeros(30720, np.float32))          # every frame silent (30720 = 120*hop) -> fill undefined
     assert e.value.code == -5
+    with pytest.raises(ainmf.AinmfError) as e:
+        ops.stft(torch.zeros((1, 20000), device="cuda"), 4096, 4096)   # > 227 KB of shared memory per block: rejected up front
+    assert "shared memory" in str(e.value)
     with pytest.raises(NotImplementedError):
         ops.stft(torch.zeros((1, 4096)), 1024, 256)             # CPU tensor: no CPU implementation
+
+
+def test_all_silent_clip_inside_a_batch_is_passed_through(ops):
+    """A clip whose every frame is flagged has no fill spectrum (NaN in the reference).  Alone it fails the call
+    (AINMF_ERR_ALL_BAD); inside a batch it is returned unchanged with err = NaN, n_iter = 0, n_bad = T, and the other
+    clips are restored exactly as they are without it."""
+    rng = np.random.default_rng(3)
+    N = 30720
+    x = (0.4 * np.sin(2 * np.pi * 440.0 * np.arange(N) / 16000.0) + 0.05 * rng.standard_normal(N)).astype(np.float32)
+    x[12000:16000] = 0
+    X = np.stack([x, np.zeros(N, np.float32), np.roll(x, 5000)])
+    y, idx, nb, W, H, err, nit = _run_columns(ops, X, max_iter=12)
+    T = idx.shape[1]
+    assert int(nb[1]) == T and int(nit[1]) == 0 and np.isnan(float(err[1]))
+    assert np.array_equal(y[1].cpu().numpy(), X[1])
+    assert np.array_equal(idx[1].cpu().numpy(), np.arange(T))
+    for b in (0, 2):
+        yb, ib, nbb, _, _, eb, nib = _run_columns(ops, X[b], max_iter=12)
+        assert torch.equal(y[b], yb[0]) and float(err[b]) == float(eb[0]) and int(nit[b]) == int(nib[0]) == 12
+        n = int(nb[b])
+        assert n == int(nbb[0]) and torch.equal(idx[b, :n], ib[0, :n]) and bool((idx[b, n:] == -1).all())
 
 
 def test_shim_classes_match_reference_interface(ops, golden, tmp_path):
