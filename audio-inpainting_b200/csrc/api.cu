@@ -106,6 +106,9 @@ struct ainmf_context {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int* poll_host = nullptr;     // pinned
+    // ainmf_inpaint_host pipeline: copy-in / compute / copy-out streams and the events that order two chunks in flight
+    cudaStream_t st_in = nullptr, st_cmp = nullptr, st_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // communicator for the time-frame-sharded mode (NCCL loaded at run time)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -418,6 +421,14 @@ int ainmf_destroy(ainmf_handle h) {
     for (Tables& t : h->tables) { cudaFree(t.tw_half); cudaFree(t.tw_full); cudaFree(t.window); }
     for (Normals& n : h->normals) { cudaFree(n.Hn); cudaFree(n.Wn); }
     if (h->scratch) cudaFree(h->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->st_in) cudaStreamDestroy(h->st_in);
+    if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
+    if (h->st_out) cudaStreamDestroy(h->st_out);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->poll_host) cudaFreeHost(h->poll_host);
     delete h;
@@ -425,6 +436,31 @@ int ainmf_destroy(ainmf_handle h) {
 }
 
 const char* ainmf_last_error(ainmf_handle h) { return h ? h->err.c_str() : g_create_error; }
+
+int ainmf_set_window(ainmf_handle h, int32_t n_fft, const float* window_host) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!is_pow2(n_fft) || n_fft < 64 || n_fft > 4096) return fail(h, AINMF_ERR_INVALID, "n_fft must be a power of two in [64, 4096], got %d", n_fft);
+    CU(h, cudaSetDevice(h->device));
+    FftTables tb;
+    int rc = get_tables(h, n_fft, &tb);                   // creates the entry (periodic Hann) on first use
+    if (rc) return rc;
+    for (Tables& t : h->tables) {
+        if (t.n_fft != n_fft) continue;
+        std::vector<float> w(n_fft);
+        double acc = 0.0;
+        const double pi = 3.14159265358979323846;
+        for (int j = 0; j < n_fft; ++j) {
+            w[j] = window_host ? window_host[j] : (float)(0.5 + 0.5 * cos(-pi + (2.0 * pi) * (double)j / (double)n_fft));
+            if (!(w[j] == w[j]) || fabsf(w[j]) > 3.0e38f) return fail(h, AINMF_ERR_INVALID, "window[%d] is not finite", j);
+            acc += (double)w[j];
+        }
+        if (!(fabs(acc) > 0.0)) return fail(h, AINMF_ERR_INVALID, "the window sums to zero: scipy's 1/sum(window) scaling is undefined");
+        CU(h, cudaDeviceSynchronize());
+        CU(h, cudaMemcpy(t.window, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+        t.win_sum = (float)acc;                           // float32 sum of the float32 window ($SP/scipy/signal/_spectral_py.py:2272-2282)
+    }
+    return AINMF_OK;
+}
 
 int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf) {
     if (!is_pow2(n_fft) || hop <= 0 || n_fft % hop != 0 || n_samples < 1) return AINMF_ERR_INVALID;
@@ -668,7 +704,11 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     if (any_work) {
         const float *Wn = nullptr, *Hn = nullptr;
         if (!W0 && (rc = get_normals(h, p->seed, K, T, F, &Wn, &Hn))) return rc;
-        for (int outer = 0; outer < p->n_outer; ++outer) {
+        // a small spectrogram (config 1: 257 x 19) runs all its refits in one launch with everything in shared memory
+        const bool small = !W0 && p->solver == AINMF_SOLVER_CD && !pl.compact && !pl.nw.use_tc && nmf_small_eligible(F, T, K) &&
+                           !getenv("AINMF_NO_SMALL");
+        if (small) CU(h, nmf_small_refit(pr, K, Wn, Hn, bad, pl.bad_stride, p->n_outer, p->max_iter, s));
+        for (int outer = 0; outer < (small ? 0 : p->n_outer); ++outer) {
             // a6: initial factors from mean(X) (sklearn draws a fresh RandomState(seed) at every fit)
             CU(h, launch_colsums(V, pl.vz_stride, ldf, F, T, B, nullptr, 0, pl.iw, s));
             CU(h, launch_mean(F, T, B, st, pl.iw, s));
@@ -723,36 +763,76 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         max_device_bytes = (size_t)1 << 30;
 #endif
     }
-    const size_t per_clip = per_clip_ws + 2 * sizeof(float) * (size_t)N + 64;
+    // Clips go through in chunks, two in flight: while chunk c is being fitted, chunk c+1 arrives on the copy-in stream and
+    // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
+    // clips and, when the batch is large enough to be worth splitting, at most half the batch -- enough tiles per launch to
+    // keep every SM busy for many rounds, small enough that only the first copy-in and the last copy-out are exposed.
+    const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256;
     long long chunk = (long long)(max_device_bytes / per_clip);
     if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
+    if (chunk > 512) chunk = 512;
+    if (p->batch >= 256 && chunk > (p->batch + 1) / 2) chunk = (p->batch + 1) / 2;
     if (chunk > p->batch) chunk = p->batch;
     ainmf_params cp = *p;
     cp.batch = (int32_t)chunk;
     const size_t ws = ainmf_workspace_bytes(h, &cp);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
-    const size_t oX = take(sizeof(float) * chunk * N), oY = take(sizeof(float) * chunk * N), oNb = take(sizeof(int) * chunk),
-                 oEr = take(sizeof(float) * chunk), oNi = take(sizeof(int) * chunk), oWs = take(ws);
+    size_t oX[2], oY[2], oNb[2], oEr[2], oNi[2];
+    for (int i = 0; i < 2; ++i) {
+        oX[i] = take(sizeof(float) * chunk * N); oY[i] = take(sizeof(float) * chunk * N);
+        oNb[i] = take(sizeof(int) * chunk); oEr[i] = take(sizeof(float) * chunk); oNi[i] = take(sizeof(int) * chunk);
+    }
+    const size_t oWs = take(ws);
     void* scr;
     int rc = get_scratch(h, o, &scr);
     if (rc) return rc;
     char* base = (char*)scr;
-    cudaStream_t s = 0;
-    for (long long b0 = 0; b0 < p->batch; b0 += chunk) {
-        const int nb = (int)((p->batch - b0 < chunk) ? p->batch - b0 : chunk);
-        cp.batch = nb;
-        CU(h, cudaMemcpyAsync(base + oX, x_host + b0 * N, sizeof(float) * (size_t)nb * N, cudaMemcpyHostToDevice, s));
-        rc = ainmf_inpaint(h, &cp, (const float*)(base + oX), nullptr, nullptr, (float*)(base + oY), nullptr,
-                           (int*)(base + oNb), nullptr, nullptr, (float*)(base + oEr), (int*)(base + oNi), base + oWs, ws, s);
-        if (rc) return rc;
-        CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY, sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, s));
-        if (n_bad_host) CU(h, cudaMemcpyAsync(n_bad_host + b0, base + oNb, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
-        if (err_host) CU(h, cudaMemcpyAsync(err_host + b0, base + oEr, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
-        if (n_iter_host) CU(h, cudaMemcpyAsync(n_iter_host + b0, base + oNi, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    if (!h->st_in) {
+        CU(h, cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->st_cmp, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
     }
-    CU(h, cudaStreamSynchronize(s));
-    return AINMF_OK;
+    const long long n_chunks = (p->batch + chunk - 1) / chunk;
+    auto chunk_size = [&](long long c) { const long long b0 = c * chunk; return (int)((p->batch - b0 < chunk) ? p->batch - b0 : chunk); };
+    auto copy_in = [&](long long c) -> int {
+        const int j = (int)(c & 1);
+        if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_in, h->ev_done[j], 0));       // the fit of chunk c-2 has read this x buffer
+        CU(h, cudaMemcpyAsync(base + oX[j], x_host + c * chunk * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
+        CU(h, cudaEventRecord(h->ev_in[j], h->st_in));
+        return 0;
+    };
+    rc = AINMF_OK;
+    if ((rc = copy_in(0))) return rc;
+    for (long long c = 0; c < n_chunks && rc == AINMF_OK; ++c) {
+        const int j = (int)(c & 1), nb = chunk_size(c);
+        const long long b0 = c * chunk;
+        if (c + 1 < n_chunks && (rc = copy_in(c + 1))) break;                      // enqueued before the fit blocks this thread at its polls
+        cp.batch = nb;
+        CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_in[j], 0));
+        if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_out[j], 0));        // the result of chunk c-2 has left this y buffer
+        rc = ainmf_inpaint(h, &cp, (const float*)(base + oX[j]), nullptr, nullptr, (float*)(base + oY[j]), nullptr,
+                           (int*)(base + oNb[j]), nullptr, nullptr, (float*)(base + oEr[j]), (int*)(base + oNi[j]), base + oWs, ws, h->st_cmp);
+        if (rc) break;
+        CU(h, cudaEventRecord(h->ev_done[j], h->st_cmp));
+        CU(h, cudaStreamWaitEvent(h->st_out, h->ev_done[j], 0));
+        CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY[j], sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
+        if (n_bad_host) CU(h, cudaMemcpyAsync(n_bad_host + b0, base + oNb[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        if (err_host) CU(h, cudaMemcpyAsync(err_host + b0, base + oEr[j], sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        if (n_iter_host) CU(h, cudaMemcpyAsync(n_iter_host + b0, base + oNi[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        CU(h, cudaEventRecord(h->ev_out[j], h->st_out));
+    }
+    // drain all three streams whatever happened, so that no copy is in flight when the caller's buffers go away
+    cudaStreamSynchronize(h->st_in);
+    cudaStreamSynchronize(h->st_cmp);
+    const cudaError_t e_out = cudaStreamSynchronize(h->st_out);
+    if (rc == AINMF_OK && e_out != cudaSuccess) return fail(h, AINMF_ERR_CUDA, "copy-out: %s", cudaGetErrorString(e_out));
+    return rc;
 }
 
 unsigned long long ainmf_launch_count(void) { return ainmf::g_launch_count; }

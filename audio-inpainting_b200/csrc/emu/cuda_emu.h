@@ -38,6 +38,7 @@ static inline int2 make_int2(int x, int y) { return {x, y}; }
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
@@ -168,6 +169,11 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 typedef void* cudaEvent_t;
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)1; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }

@@ -212,6 +212,12 @@ cudaError_t nmf_mu_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaS
 // PARTIALS: HHt and X.Ht of the local frames; UPDATE: W sweep, WtW, fused X^T.W + H sweep; STOP: the stop rule
 cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s);
 cudaError_t launch_set_err(ClipState* st, int B, const double* err_sq, cudaStream_t s);
+// ---- nmf_small.cu: a small spectrogram's whole fit -- and main4_NMF.py's chain of n_outer refits -- in one launch, one CTA
+// per clip, everything in shared memory (seeded initial factors).  bad: frames replaced by (W H)
+// after each fit.  On return Xt holds the restored frames, W / Ht the last fit's factors, state n_iter / err.
+bool nmf_small_eligible(int F, int T, int K);      // K = the rank itself, not the padded one
+cudaError_t nmf_small_refit(const NmfProblem& p, int K, const float* Wn, const float* Hn, const unsigned char* bad, long long bad_stride,
+                            int n_outer, int max_iter, cudaStream_t s);
 // err = ||X - W H||_F into state[b].err, then bad frames of Xt <- (W H) frames
 cudaError_t nmf_finalize(const NmfProblem& p, const NmfWork& wk, const unsigned char* bad, long long bad_stride,
                          cudaStream_t s, double* err_sq = nullptr);

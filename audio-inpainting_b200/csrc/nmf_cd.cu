@@ -330,6 +330,8 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
             }
         }
         __syncthreads();
+        // F = 2^m + 1 leaves the last block of a clip with one row: warps without a valid row skip the sweep
+        if (__ballot_sync(0xffffffffu, valid) != 0u) {
 #pragma unroll
         for (int t = 0; t < KP; ++t) {
             const float* gr = sG + t * GP;
@@ -353,6 +355,7 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
             vsum += valid ? fabsf(pg) : 0.f;
             if (pg_out && valid) pg_out[((long long)b * F + f) * KP + t] = fabsf(pg);
             if (valid && inv != 0.f) a[t] = fmaxf(fmaf(-grad, inv, aq), 0.f);
+        }
         }
 #pragma unroll
         for (int q = 0; q < KP; q += 4) *reinterpret_cast<float4*>(ar + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
@@ -481,7 +484,7 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                 for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
             const int c0 = pass * 16 * TJ + tx * TJ;
 #pragma unroll 2
-            for (int rr = 0; rr < ROWS; ++rr) {
+            for (int rr = 0; rr < rows_here; ++rr) {        // rows past the clip's last one are zero
                 const float* row = sA + rr * AP;
                 float fi[TI], fj[TJ];
                 if constexpr (TI % 4 == 0) {
@@ -1321,7 +1324,7 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
     }
 #endif
     // small FFMA-path problems keep |pg| per (row, coordinate) for the reference-order violation sum (stop_kernel)
-    wk->exact_viol = (!wk->use_tc && (long long)B * ((long long)F + T) * KP <= (1LL << 20)) ? 1 : 0;
+    wk->exact_viol = (!wk->use_tc && ((long long)B * ((long long)F + T) * KP <= (1LL << 20))) ? 1 : 0;
 }
 
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {

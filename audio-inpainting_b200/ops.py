@@ -276,6 +276,23 @@ def apply_gaps_(x, starts, lens):
     return x
 
 
+def set_window(n_fft, window=None, device=None):
+    """The `window` argument of scipy.signal.stft / istft for every later call with this n_fft on `device` (default: the
+    current CUDA device): an array-like of n_fft values, or None for scipy's default periodic Hann window (what the
+    reference runs, main4_NMF_gap.py:47,71).  ainmf_set_window."""
+    import numpy as np
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    L = _lib.lib()
+    ptr = None
+    if window is not None:
+        w = np.ascontiguousarray(np.asarray(window, dtype=np.float32))
+        if w.shape != (n_fft,):
+            raise RuntimeError(f"window must hold n_fft = {n_fft} values, got shape {w.shape}")
+        ptr = w.ctypes.data_as(C.c_void_p)
+    with torch.cuda.device(dev):
+        _lib.check(L.ainmf_set_window(_lib.handle(dev), int(n_fft), ptr), dev)
+
+
 def snr_db(ref, est, begin=0, end=None):
     """10 log10(sum ref^2 / (sum (ref - est)^2 + 1e-10)) over [begin, end) (main4_NMF.py:99-110); returns a Python float."""
     ref, est = _f32(ref, "ref"), _f32(est, "est")

@@ -77,9 +77,17 @@ void ainmf_params_default(ainmf_params* p);     /* the constants of main4_NMF_ga
 int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf);
 int32_t ainmf_padded_rank(int32_t rank);        /* 32, 64 or 128 */
 
+/* ---- window -------------------------------------------------------------------------------------------- */
+/* The `window` argument of scipy.signal.stft / istft (the reference passes none: main4_NMF_gap.py:47,71 run scipy's default,
+ * the periodic Hann window, which is what every call uses until this is called).  window_host: n_fft float32 values on the
+ * HOST (what np.asarray(window, float32) holds), or NULL to go back to the periodic Hann window.  It applies to every later
+ * ainmf_stft / ainmf_istft / ainmf_inpaint* call of this handle with that n_fft; the same window analyses and synthesises,
+ * as in scipy, so it must satisfy NOLA for the hop in use.  Call it while no work of this handle is in flight. */
+int ainmf_set_window(ainmf_handle h, int32_t n_fft, const float* window_host);
+
 /* ---- stage entry points (device buffers) --------------------------------------------------------------- */
 /* signal.stft + np.abs (main4_NMF_gap.py:47-48).  mag_ft [B][F][T] float, Z_ft [B][F][T] complex64 (re,im). Either
- * may be NULL.  The window is periodic Hann, scipy's default. */
+ * may be NULL.  The window is periodic Hann, scipy's default, unless ainmf_set_window installed another. */
 int ainmf_stft(ainmf_handle h, const float* x, int32_t batch, int64_t n_samples, int32_t n_fft, int32_t hop,
                float* mag_ft, float* Z_ft, void* stream);
 

@@ -60,6 +60,30 @@ def test_istft_matches_scipy(ops, N, n_fft, hop):
     assert rel_l2(y, ys[:N]) <= 1e-5
 
 
+def test_window_argument_matches_scipy(ops):
+    """north_star lists `window` among the arguments of the path: a caller-supplied window (here Hamming and a Tukey-shaped
+    array) must give scipy's stft / istft with `window=array`; None restores the periodic Hann default."""
+    from scipy import signal
+    rng = np.random.default_rng(4)
+    n_fft, hop, N = 512, 128, 20000
+    x = rng.standard_normal(N).astype(np.float32)
+    try:
+        for w in (signal.get_window("hamming", n_fft), signal.get_window(("tukey", 0.7), n_fft) + 0.05):
+            ops.set_window(n_fft, w)
+            mag, Z = ops.stft(dev(x[None]), n_fft, hop)
+            _, _, Zs = signal.stft(x, SR, window=w.astype(np.float32), nperseg=n_fft, noverlap=n_fft - hop)
+            assert rel_l2(Z[0].cpu().numpy(), Zs) <= 1e-5
+            Zm = (Zs * (1 + 0.2 * rng.standard_normal(Zs.shape))).astype(np.complex64)
+            _, ys = signal.istft(Zm, SR, window=w.astype(np.float32), nperseg=n_fft, noverlap=n_fft - hop)
+            y = ops.istft(dev(Zm[None]), n_fft, hop, N)[0].cpu().numpy()
+            assert rel_l2(y, ys[:N]) <= 1e-5
+    finally:
+        ops.set_window(n_fft, None)
+    _, Z = ops.stft(dev(x[None]), n_fft, hop)
+    _, _, Zs = signal.stft(x, SR, nperseg=n_fft, noverlap=n_fft - hop)
+    assert rel_l2(Z[0].cpu().numpy(), Zs) <= 1e-5
+
+
 def test_stft_istft_round_trip_full_size(ops):
     """Size-independent property at BASELINE sizes: istft(stft(x)) == x (NOLA holds for Hann, 75 % overlap)."""
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -416,6 +440,51 @@ def test_all_silent_clip_inside_a_batch_is_passed_through(ops):
         assert torch.equal(y[b], yb[0]) and float(err[b]) == float(eb[0]) and int(nit[b]) == int(nib[0]) == 12
         n = int(nb[b])
         assert n == int(nbb[0]) and torch.equal(idx[b, :n], ib[0, :n]) and bool((idx[b, n:] == -1).all())
+
+
+def test_host_entry_point_pipelines_chunks_and_matches_the_device_op(ops):
+    """ainmf_inpaint_host splits a batch into chunks with two in flight (copy-in | fit | copy-out on three streams).  Clips
+    are independent, so the chunked host call must return for every clip what one device call on the whole batch returns --
+    same frame counts and iteration counts, objective within 1e-5, waveform within 90 dB (the kernels pick their split
+    factors from the batch size, so the floating-point summation order differs between a 300-clip and a 150-clip launch;
+    a lost dependency between the three streams would show up as garbage, not as 1e-6) -- for the default split
+    (300 clips -> 150 + 150) and for a memory cap that forces many small chunks with buffer reuse."""
+    import ctypes as C
+    import ainmf
+    from ainmf import _capi
+    rng = np.random.default_rng(8)
+    B, N = 300, 12000
+    t = np.arange(N) / 8000.0
+    X = np.empty((B, N), np.float32)
+    for b in range(B):
+        x = np.sin(2 * np.pi * rng.uniform(200, 1500) * t) + 0.3 * np.sin(2 * np.pi * rng.uniform(1500, 3500) * t) + 0.05 * rng.standard_normal(N)
+        x = (x / np.abs(x).max()).astype(np.float32)
+        if b % 7 != 3:                                   # every seventh clip has nothing to restore
+            s0 = int(rng.integers(500, N - 3000))
+            x[s0:s0 + int(rng.integers(300, 2000))] = 0
+        X[b] = x
+    yd, idx, nbd, W, H, errd, nitd = ops.nmf_inpaint(dev(X), 256, 64, 16, 25, 0.0, 42, 1e-4, 9, 10, -1, -1, 1, None, None)
+    L = ainmf._lib.lib()
+    h = ainmf._lib.handle(0)
+    p = _capi.default_params(L, batch=B, n_samples=N, n_fft=256, hop=64, rank=16, max_iter=25, tol=0.0, seed=42,
+                             threshold=1e-4, frac_num=9, frac_den=10)
+    xh = torch.from_numpy(X).pin_memory()
+    ydn, errn = yd.cpu().numpy(), errd.cpu().numpy()
+    for cap in (0, 40 << 20):                            # default chunking (150 + 150); 40 MB cap -> many chunks, buffers reused
+        yh = torch.zeros((B, N), dtype=torch.float32).pin_memory()
+        nb, er, ni = np.zeros(B, np.int32), np.zeros(B, np.float32), np.zeros(B, np.int32)
+        rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), nb.ctypes.data_as(C.c_void_p),
+                                  er.ctypes.data_as(C.c_void_p), ni.ctypes.data_as(C.c_void_p), cap)
+        ainmf._lib.check(rc, 0)
+        assert np.array_equal(nb, nbd.cpu().numpy()) and np.array_equal(ni, nitd.cpu().numpy())
+        yn = yh.numpy()
+        for b in range(B):
+            if nb[b] == 0:
+                assert np.array_equal(yn[b], X[b])
+            else:
+                assert abs(er[b] - errn[b]) <= 1e-5 * errn[b]
+                assert libcalls.snr_db(ydn[b], yn[b]) >= 90.0
+    assert int((nbd == 0).sum()) >= 30 and int((nbd > 0).sum()) >= 200
 
 
 def test_shim_classes_match_reference_interface(ops, golden, tmp_path):

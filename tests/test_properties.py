@@ -75,5 +75,5 @@ def test_cd_sweep_never_increases_the_objective_and_keeps_factors_nonnegative(F,
         restate.cd_sweep(W, (Ht.T @ Ht).astype(np.float32), (X @ Ht).astype(np.float32))
         restate.cd_sweep(Ht, (W.T @ W).astype(np.float32), (X.T @ W).astype(np.float32))
         cur = obj(W, Ht)
-        assert cur <= prev * (1 + 1e-5) and W.min() >= 0 and Ht.min() >= 0
+        assert cur <= prev * (1 + 1e-5) + 1e-6 * float(np.linalg.norm(X)) and W.min() >= 0 and Ht.min() >= 0   # (an exact fit sits at rounding noise)
         prev = cur
