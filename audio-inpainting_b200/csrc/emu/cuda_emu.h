@@ -65,6 +65,7 @@ inline thread_local unsigned t_linear = 0;
 
 static inline void __syncthreads() { emu::ctx()->block_bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx()->warp_bar[emu::t_linear / 32]->arrive_and_wait(); }
+static inline long long clock64() { return 0; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 namespace emu {
