@@ -507,6 +507,13 @@ h_step_ts_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 //   MMA:  per 8 frames one kind::tf32 (A from TMEM, B = raw Ht chunk) and one kind::f16 instruction (cross terms);
 //   epilogue warps store finished accumulators (double-buffered) to the partial buffers.
 // =====================================================================================================
+// role layout of the X.Ht kernel: its converters also build the B cross operand, about twice the H step's work per chunk
+// (three groups at K = 64 were measured slower than two: 72 registers per thread, X.Ht 0.55 instead of 0.52 ms)
+template <int KP> struct XtShape {
+    static constexpr int CONV_GROUPS = (KP == 64) ? 2 : 1;
+    static constexpr int SWEEP_WARP0 = 4 + 4 * CONV_GROUPS;      // first epilogue warp
+    static constexpr int THREADS = 32 * (SWEEP_WARP0 + 4);
+};
 template <int KP> struct XtCfg {
     static constexpr int NSS = (KP == 64) ? 5 : 3;               // shared-memory stages
     static constexpr int NAS = (KP == 64) ? 5 : 3;               // TMEM A stages
@@ -537,12 +544,14 @@ struct XtItems {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(TsShape<KP>::THREADS, 1)
+__global__ void __launch_bounds__(XtShape<KP>::THREADS, 1)
 xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__ CUtensorMap mapHs,
               const __grid_constant__ CUtensorMap mapHmn, int F, int T, int B, int S, int mtiles, int frames_per_split,
               float* __restrict__ xht_partial /*[B][S][F][KP]*/, float* __restrict__ gram_partial /*[B][S][KP][KP]*/,
-              const ClipState* __restrict__ st, const int* __restrict__ t_good /*good-first frame order or null*/) {
+              const ClipState* __restrict__ st, const int* __restrict__ t_good /*good-first frame order or null*/,
+              long long* __restrict__ dbg /*AINMF_TC_DEBUG=1: wait / work cycles of CTA 0's roles, or null*/) {
     using Cfg = XtCfg<KP>;
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 0;
     constexpr int NSS = Cfg::NSS, NAS = Cfg::NAS, NB = KP / 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) TsBarriers bars;
@@ -578,11 +587,14 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
     if (warp == 0) {
         if (elect_one()) {
             uint32_t it = 0;
+            long long p_w = 0, p_t = 0;
             while (items.next(b, split, mt)) {
                 const int nk = chunks_of(b, split, mt), t_begin = split * frames_per_split;
                 for (int i = 0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS;
+                    if (dbg_on) p_t = clock64();
                     mbar_wait(&bars.empty[s], ((it / NSS) & 1) ^ 1);
+                    if (dbg_on) p_w += clock64() - p_t;
                     unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
                     const int t0 = t_begin + i * TS_BK;           // frames past T load zeros; split boundaries are multiples of 32
                     mbar_arrive_expect_tx(&bars.full[s], Cfg::A_BYTES + 2 * Cfg::B_BYTES);
@@ -599,21 +611,28 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                     }
                 }
             }
+            if (dbg_on) { dbg[0] = p_w; dbg[1] = it; }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(TS_M, KP, 0, 1), idesc16 = make_idesc_bf16(TS_M, KP, 0, 0);
             uint32_t it = 0, tl = 0;
+            long long q_d = 0, q_c = 0, q_f = 0, q_i = 0, q_t = 0;
             while (items.next(b, split, mt)) {
                 const int nk = chunks_of(b, split, mt);
                 const uint32_t buf = tl & 1;
+                if (dbg_on) q_t = clock64();
                 mbar_wait(&bars.dempty[buf], ((tl >> 1) & 1) ^ 1);
+                if (dbg_on) q_d += clock64() - q_t;
                 tcgen05_fence_after();
                 const uint32_t dcol = tmem + Cfg::COL_D + buf * KP;
                 for (int i = 0; i < nk; ++i, ++it) {
                     const uint32_t s = it % NSS, a = it % NAS;
+                    if (dbg_on) q_t = clock64();
                     mbar_wait(&bars.conv[a], (it / NAS) & 1);       // the converters waited for full[s] themselves
+                    if (dbg_on) { const long long c = clock64(); q_c += c - q_t; q_t = c; }
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
+                    if (dbg_on) { const long long c = clock64(); q_f += c - q_t; q_t = c; }
                     tcgen05_fence_after();
                     const uint32_t b_raw = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
                     const uint64_t d_bx = make_smem_desc(b_raw + 2 * Cfg::B_BYTES, 16, 1024);
@@ -626,28 +645,34 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                     }
                     mma_commit(&bars.empty[s]);
                     mma_commit(&bars.aempty[a]);
+                    if (dbg_on) q_i += clock64() - q_t;
                 }
                 mma_commit(&bars.dfull[buf]);
                 ++tl;
             }
+            if (dbg_on) { dbg[2] = q_d; dbg[3] = q_c; dbg[4] = q_f; dbg[5] = q_i; dbg[6] = it; dbg[7] = tl; }
         }
-    } else if (warp >= 4 && warp < TsShape<KP>::SWEEP_WARP0) {
-        // two converter groups (warps 4-7, 8-11) take alternate chunks, as in the H step
+    } else if (warp >= 4 && warp < XtShape<KP>::SWEEP_WARP0) {
+        // converter groups of 4 warps take the chunks round-robin, as in the H step
         const int q = warp & 3, col = q * 32 + lane;
         const uint32_t grp = (warp - 4) >> 2;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + Cfg::COL_A;
         uint32_t it = 0;
+        long long k_w = 0, k_a = 0, k_b = 0, k_s = 0, k_n = 0, k_t = 0;
+        const bool kd = dbg_on && col == 0;
         while (items.next(b, split, mt)) {
             const int nk = chunks_of(b, split, mt);
             for (int i = 0; i < nk; ++i, ++it) {
-                if ((it & (uint32_t)(TsShape<KP>::CONV_GROUPS - 1)) != grp) continue;
+                if (it % (uint32_t)XtShape<KP>::CONV_GROUPS != grp) continue;
                 const uint32_t s = it % NSS, a = it % NAS;
+                if (kd) k_t = clock64();
                 if (lane == 0) {
                     mbar_wait(&bars.full[s], (it / NSS) & 1);
                     mbar_wait(&bars.aempty[a], ((it / NAS) & 1) ^ 1);
                 }
                 __syncwarp();
                 tcgen05_fence_after();
+                if (kd) { const long long c = clock64(); k_w += c - k_t; k_t = c; }
                 unsigned char* stg = smem + (size_t)s * Cfg::STAGE_BYTES;
                 {   // A: column `col` of the tile over the chunk's 32 frames
                     const float* xs = reinterpret_cast<const float*>(stg + q * Cfg::SLAB) + lane;
@@ -659,6 +684,7 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                     tmem_st_32x32(tlane + a * 64, hi);
                     tmem_st_32x32(tlane + a * 64 + 32, cx);
                 }
+                if (kd) { const long long c = clock64(); k_a += c - k_t; k_t = c; }
                 if (col < KP) {   // B cross operand: row n = col, 4 groups of 8 frames -> 8 chunks of 16 bytes (128-byte swizzle)
                     const float* hs = reinterpret_cast<const float*>(stg + Cfg::A_BYTES + Cfg::B_BYTES + (col >> 5) * Cfg::SLAB) + (col & 31);
                     unsigned char* br = stg + Cfg::A_BYTES + 2 * Cfg::B_BYTES + col * 128;
@@ -673,13 +699,16 @@ xht_ts_kernel(const __grid_constant__ CUtensorMap mapXs, const __grid_constant__
                     }
                     fence_proxy_async_smem();
                 }
+                if (kd) { const long long c = clock64(); k_b += c - k_t; k_t = c; }
                 tmem_wait_st();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars.conv[a]);
+                if (kd) { k_s += clock64() - k_t; ++k_n; }
             }
         }
-    } else if (warp >= TsShape<KP>::SWEEP_WARP0) {
+        if (kd && grp == 0) { dbg[8] = k_w; dbg[9] = k_a; dbg[10] = k_b; dbg[11] = k_s; dbg[12] = k_n; }
+    } else if (warp >= XtShape<KP>::SWEEP_WARP0) {
         // ---------------- epilogue: rows of the accumulator straight to the partial buffers ----------------
         const int q = warp & 3;
         uint32_t tl = 0;
@@ -791,8 +820,28 @@ static cudaError_t ts_half1_impl(const NmfProblem& p, const NmfWork& wk, cudaStr
     }
     const long long items = (long long)p.B * wk.tc_splits * wk.tc_mtiles;
     const int grid = (int)(items < n_sm ? items : n_sm);
-    AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(TsShape<KP>::THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
-                 as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state, p.t_good);
+    static long long* dbg = nullptr;
+    static int dbg_left = -1;
+    if (dbg_left < 0) {
+        const char* e_ = getenv("AINMF_TC_DEBUG");
+        dbg_left = (e_ && e_[0] == '1') ? 2 : 0;
+        if (dbg_left) cudaMalloc((void**)&dbg, 16 * sizeof(long long));
+    }
+    if (dbg_left > 0) cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), s);
+    AINMF_LAUNCH(xht_ts_kernel<KP>, dim3(grid), dim3(XtShape<KP>::THREADS), Cfg::SMEM_BYTES, s, as_map(wk.tc->mapXs), as_map(wk.tc->mapHs),
+                 as_map(wk.tc->mapHmn), p.F, p.T, p.B, wk.tc_splits, wk.tc_mtiles, wk.tc_fps, wk.xht_partial, wk.gram_partial, p.state, p.t_good,
+                 dbg_left > 0 ? dbg : nullptr);
+    if (dbg_left > 0) {
+        --dbg_left;
+        long long hb[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hb, dbg, sizeof hb, cudaMemcpyDeviceToHost);
+        const double n = hb[6] > 0 ? (double)hb[6] : 1.0, nc = hb[12] > 0 ? (double)hb[12] : 1.0;
+        fprintf(stderr, "[ts-debug xht KP=%d grid=%d items=%lld] CTA 0: %lld chunks in %lld items; cycles per chunk: producer waits for a free stage %.0f | "
+                        "issuer: accumulator free %.0f, converters %.0f, TMA %.0f, issue+commit %.0f | converter group 0 (per chunk it takes): waits %.0f, A operand %.0f, "
+                        "B cross operand %.0f, st visible + arrive %.0f\n", KP, grid, items, hb[6], hb[7], hb[0] / n, hb[2] / n, hb[3] / n, hb[4] / n, hb[5] / n,
+                hb[8] / nc, hb[9] / nc, hb[10] / nc, hb[11] / nc);
+    }
     return cudaGetLastError();
 }
 cudaError_t nmf_ts_half1(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
