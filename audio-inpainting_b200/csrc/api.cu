@@ -17,6 +17,7 @@ using namespace ainmf;
 
 namespace {
 
+#ifdef AINMF_EMU
 // ---- host RNG: numpy RandomState(seed).standard_normal --------------------------------------------------
 // MT19937 seeded with init_genrand, 53-bit doubles, polar Box-Muller with the cached second deviate
 // (numpy/random/src/legacy/legacy-distributions.c: legacy_gauss) -- what _initialize_nmf(init='random')
@@ -76,6 +77,8 @@ void standard_normal_f32(uint32_t seed, float* out, size_t n) {
     }
 }
 
+#endif  // AINMF_EMU (the CUDA build draws them on the device, rng.cu)
+
 struct Tables {
     int n_fft = 0;
     float2* tw_half = nullptr;
@@ -86,8 +89,8 @@ struct Tables {
 
 struct Normals {
     uint32_t seed = 0;
-    int K = 0, T = 0, F = 0;
-    float* Hn = nullptr;   // [K][T] device
+    int K = 0, T = 0, F = 0, t_begin = 0, t_count = 0;
+    float* Hn = nullptr;   // [K][t_count] device: frames [t_begin, t_begin + t_count) of the (K, T) draw
     float* Wn = nullptr;   // [F][K] device
 };
 
@@ -194,24 +197,35 @@ int get_tables(ainmf_handle h, int n_fft, FftTables* out) {
     return 0;
 }
 
-// Device copies of the normals sklearn would draw for (seed, K, T, F): H (K,T) first, then W (F,K).
-int get_normals(ainmf_handle h, uint32_t seed, int K, int T, int F, const float** Wn, const float** Hn) {
+// The normals sklearn would draw for (seed, K, T, F): H (K,T) first, then W (F,K); of H only frames [t_begin, t_begin +
+// t_count) are kept (a rank of the time-sharded mode needs its own frames only).  Generated on the device (rng.cu) on the
+// caller's stream and cached in the handle; the host generator above serves the emulator build.
+int get_normals(ainmf_handle h, uint32_t seed, int K, int T, int F, int t_begin, int t_count, const float** Wn, const float** Hn,
+                cudaStream_t s) {
     for (const Normals& n : h->normals)
-        if (n.seed == seed && n.K == K && n.T == T && n.F == F) { *Wn = n.Wn; *Hn = n.Hn; return 0; }
-    if (h->normals.size() >= 4) {      // small cache: evict the oldest
+        if (n.seed == seed && n.K == K && n.T == T && n.F == F && n.t_begin == t_begin && n.t_count == t_count) { *Wn = n.Wn; *Hn = n.Hn; return 0; }
+    if (h->normals.size() >= 4) {      // small cache: evict the oldest (after everything queued on it has run)
+        cudaDeviceSynchronize();
         cudaFree(h->normals[0].Hn);
         cudaFree(h->normals[0].Wn);
         h->normals.erase(h->normals.begin());
     }
-    const size_t nH = (size_t)K * T, nW = (size_t)F * K;
-    std::vector<float> z(nH + nW);
-    standard_normal_f32(seed, z.data(), nH + nW);
+    const size_t nH = (size_t)K * t_count, nW = (size_t)F * K;
     Normals n;
-    n.seed = seed; n.K = K; n.T = T; n.F = F;
+    n.seed = seed; n.K = K; n.T = T; n.F = F; n.t_begin = t_begin; n.t_count = t_count;
     CU(h, cudaMalloc((void**)&n.Hn, sizeof(float) * nH));
     CU(h, cudaMalloc((void**)&n.Wn, sizeof(float) * nW));
-    CU(h, cudaMemcpy(n.Hn, z.data(), sizeof(float) * nH, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(n.Wn, z.data() + nH, sizeof(float) * nW, cudaMemcpyHostToDevice));
+#ifdef AINMF_EMU
+    {
+        std::vector<float> z((size_t)K * T + nW), hl(nH);
+        standard_normal_f32(seed, z.data(), z.size());
+        for (int k = 0; k < K; ++k) memcpy(hl.data() + (size_t)k * t_count, z.data() + (size_t)k * T + t_begin, sizeof(float) * t_count);
+        CU(h, cudaMemcpy(n.Hn, hl.data(), sizeof(float) * nH, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(n.Wn, z.data() + (size_t)K * T, sizeof(float) * nW, cudaMemcpyHostToDevice));
+    }
+#else
+    CU(h, launch_numpy_normals(seed, K, T, t_begin, t_count, n.Hn, F, n.Wn, s));
+#endif
     h->normals.push_back(n);
     *Wn = n.Wn; *Hn = n.Hn;
     return 0;
@@ -462,6 +476,20 @@ int ainmf_set_window(ainmf_handle h, int32_t n_fft, const float* window_host) {
     return AINMF_OK;
 }
 
+int ainmf_standard_normal(ainmf_handle h, uint32_t seed, int64_t n, float* out, void* stream) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!out || n < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_standard_normal");
+    CU(h, cudaSetDevice(h->device));
+#ifdef AINMF_EMU
+    std::vector<float> z((size_t)n);
+    standard_normal_f32(seed, z.data(), z.size());
+    CU(h, cudaMemcpy(out, z.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+#else
+    CU(h, launch_numpy_normals(seed, 1, n, 0, n, out, 0, nullptr, (cudaStream_t)stream));
+#endif
+    return AINMF_OK;
+}
+
 int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf) {
     if (!is_pow2(n_fft) || hop <= 0 || n_fft % hop != 0 || n_samples < 1) return AINMF_ERR_INVALID;
     StftGeom g;
@@ -568,7 +596,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
         CU(h, launch_pack_factors(W0, H0, B, F, T, rank, KP, pr.W, ws, pr.Ht, hs, s));
     } else {
         const float *Wn, *Hn;
-        if ((rc = get_normals(h, seed, rank, T, F, &Wn, &Hn))) return rc;
+        if ((rc = get_normals(h, seed, rank, T, F, 0, T, &Wn, &Hn, s))) return rc;
         CU(h, launch_init_factors(Wn, Hn, T, 0, B, F, T, rank, KP, pr.state, pr.W, ws, pr.Ht, hs, s));
     }
     if ((rc = run_iterations(h, pr, nw, max_iter, tol, (int*)(base + oF), s))) return rc;
@@ -703,7 +731,7 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     const bool any_work = h->poll_host[2] > 0;
     if (any_work) {
         const float *Wn = nullptr, *Hn = nullptr;
-        if (!W0 && (rc = get_normals(h, p->seed, K, T, F, &Wn, &Hn))) return rc;
+        if (!W0 && (rc = get_normals(h, p->seed, K, T, F, 0, T, &Wn, &Hn, s))) return rc;
         // a small spectrogram (config 1: 257 x 19) runs all its refits in one launch with everything in shared memory
         const bool small = !W0 && p->solver == AINMF_SOLVER_CD && !pl.compact && !pl.nw.use_tc && nmf_small_eligible(F, T, K) &&
                            !getenv("AINMF_NO_SMALL");

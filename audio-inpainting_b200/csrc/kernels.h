@@ -77,6 +77,12 @@ cudaError_t launch_blend(const float* raw, const float* restored, long long N, l
                          float* out, cudaStream_t s);
 cudaError_t launch_snr_sums(const float* ref, const float* est, long long begin, long long end, double* sums, cudaStream_t s);
 
+// ---- rng.cu: RandomState(seed).standard_normal on the device ------------------------------------------------------------
+// The K*T_total normals of H0 (row-major (K, T_total); only frames [t_begin, t_begin + t_count) are kept, as Hn[K][t_count])
+// followed by the F*K normals of W0 (Wn[F][K]) -- the order sklearn draws them in (_nmf.py:296-307).
+cudaError_t launch_numpy_normals(uint32_t seed, int K, long long T_total, long long t_begin, long long t_count, float* Hn, int F, float* Wn,
+                                 cudaStream_t s);
+
 // ---- per-clip control block (device) ---------------------------------------------------------------
 struct ClipState {
     int done;            // 1 once the stop rule fired (or nothing to do); kernels of the iteration skip the clip

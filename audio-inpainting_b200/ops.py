@@ -276,6 +276,17 @@ def apply_gaps_(x, starts, lens):
     return x
 
 
+def standard_normal(seed, n, device=None):
+    """float32(numpy.random.RandomState(seed).standard_normal(n)) generated on the device (ainmf_standard_normal): the stream
+    sklearn's init='random' draws H0 then W0 from."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = torch.empty((int(n),), dtype=torch.float32, device=torch.device("cuda", dev))
+        _lib.check(L.ainmf_standard_normal(_lib.handle(dev), int(seed) & 0xFFFFFFFF, int(n), _p(out), _stream(dev)), dev)
+    return out
+
+
 def set_window(n_fft, window=None, device=None):
     """The `window` argument of scipy.signal.stft / istft for every later call with this n_fft on `device` (default: the
     current CUDA device): an array-like of n_fft values, or None for scipy's default periodic Hann window (what the

@@ -77,6 +77,13 @@ void ainmf_params_default(ainmf_params* p);     /* the constants of main4_NMF_ga
 int ainmf_stft_geometry(int64_t n_samples, int32_t n_fft, int32_t hop, int32_t* T, int32_t* F, int32_t* ldf);
 int32_t ainmf_padded_rank(int32_t rank);        /* 32, 64 or 128 */
 
+/* ---- initial factors ---------------------------------------------------------------------------------- */
+/* out[i] = float32(numpy.random.RandomState(seed).standard_normal(n)[i]) on the device: MT19937 + the legacy polar Gaussian,
+ * the stream sklearn's init='random' draws its factors from ($SP/sklearn/decomposition/_nmf.py:296-307: H0 = |avg * N((K, T))|
+ * first, then W0 = |avg * N((F, K))|, avg = sqrt(mean(X) / K)).  ainmf_nmf_fit / ainmf_inpaint use it internally when W0/H0
+ * are NULL; it is exported for callers that build W0/H0 themselves.  One thread block walks the stream: ~2 ns per normal. */
+int ainmf_standard_normal(ainmf_handle h, uint32_t seed, int64_t n, float* out, void* stream);
+
 /* ---- window -------------------------------------------------------------------------------------------- */
 /* The `window` argument of scipy.signal.stft / istft (the reference passes none: main4_NMF_gap.py:47,71 run scipy's default,
  * the periodic Hann window, which is what every call uses until this is called).  window_host: n_fft float32 values on the

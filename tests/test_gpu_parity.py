@@ -207,6 +207,19 @@ def test_nmf_fit_seeded_init_and_early_stop(ops):
     assert rel_l2(W1[0].cpu().numpy(), Wo1) < 1e-5 and rel_l2(H1[0].cpu().numpy(), Ho1) < 1e-5
 
 
+@pytest.mark.parametrize("seed,n", [(0, 7), (42, 100003), (0, 3000000), (123456789, 624 * 7 + 1)])
+def test_device_rng_is_numpy_randomstate(ops, seed, n):
+    """The initial factors come from RandomState(seed).standard_normal: MT19937 + the legacy polar method with its cached
+    second deviate.  The device generator must reproduce numpy's float32 values -- bit for bit except where CUDA's and
+    glibc's double log differ in the last bit AND that bit decides a float32 rounding (probability ~1e-9 per value)."""
+    want = np.random.RandomState(seed).standard_normal(n).astype(np.float32)
+    got = ops.standard_normal(seed, n).cpu().numpy()
+    assert got.shape == want.shape
+    same = got.view(np.uint32) == want.view(np.uint32)
+    assert same.mean() >= 1 - 2e-6, (int((~same).sum()), n)
+    assert np.max(np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))) <= 1      # at most one float32 ulp
+
+
 def test_nmf_fit_batch_is_independent(ops):
     rng = np.random.default_rng(5)
     X = np.abs(rng.standard_normal((3, 129, 200))).astype(np.float32)
