@@ -109,6 +109,7 @@ struct ainmf_context {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int* poll_host = nullptr;     // pinned
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};   // stop-flag polls, one group of iterations behind the launches
     // ainmf_inpaint_host pipeline: copy-in / compute / copy-out streams and the events that order two chunks in flight
     cudaStream_t st_in = nullptr, st_cmp = nullptr, st_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -365,21 +366,33 @@ __global__ void copy_indices_kernel(const int* __restrict__ idx, const ClipState
     if (t < T) out[(long long)b * T + t] = (t < st[b].n_bad) ? idx[(long long)b * T + t] : -1;
 }
 
-// Runs up to max_iter iterations, polling the stop flags every `poll` iterations when tol > 0.
+// Runs up to max_iter iterations.  When tol > 0 the number of clips still iterating is read back every `poll` iterations,
+// but the host looks at the answer of group g only after it has queued group g + 1: the stream never drains while the host
+// waits and launches.  Kernels skip clips whose stop rule fired (ClipState.done, set on the device), so the up to `poll`
+// extra iterations queued after the last clip converged do nothing and every clip's n_iter is exact.
 int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, int max_iter, float tol, int* d_flag,
                    cudaStream_t s) {
     const bool mu = prob.solver == AINMF_SOLVER_MU;
     const int poll = mu ? 10 : 8;          // MU tests convergence every 10th iteration only
     if (mu && tol > 0.f) CU(h, nmf_mu_begin(prob, nw, s));
+    if (tol > 0.f && !h->ev_poll[0])
+        for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
+    int pending = -1;
     for (int it = 1; it <= max_iter; ++it) {
         if (mu) CU(h, nmf_mu_iterate(prob, nw, it, s));
         else CU(h, nmf_cd_iterate(prob, nw, it, s));
         if (tol > 0.f && (it % poll == 0) && it < max_iter) {
-            AINMF_LAUNCH(count_not_done_kernel, dim3(1), dim3(kThreads), 0, s, prob.state, prob.B, d_flag);
+            const int g = (it / poll) & 1;
+            int* d_out = d_flag + (g ? 3 : 0);
+            AINMF_LAUNCH(count_not_done_kernel, dim3(1), dim3(kThreads), 0, s, prob.state, prob.B, d_out);
             CU(h, cudaGetLastError());
-            CU(h, cudaMemcpyAsync(h->poll_host, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CU(h, cudaStreamSynchronize(s));
-            if (h->poll_host[0] == 0) break;
+            CU(h, cudaMemcpyAsync(h->poll_host + 8 + g, d_out, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CU(h, cudaEventRecord(h->ev_poll[g], s));
+            if (pending >= 0) {
+                CU(h, cudaEventSynchronize(h->ev_poll[pending]));
+                if (h->poll_host[8 + pending] == 0) break;
+            }
+            pending = g;
         }
     }
     return 0;
@@ -436,6 +449,7 @@ int ainmf_destroy(ainmf_handle h) {
     for (Normals& n : h->normals) { cudaFree(n.Hn); cudaFree(n.Wn); }
     if (h->scratch) cudaFree(h->scratch);
     for (int i = 0; i < 2; ++i) {
+        if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);

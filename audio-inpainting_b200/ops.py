@@ -9,6 +9,8 @@ Shapes follow the reference's arrays: spectrogram-like tensors are (B, F, T) as 
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 
 import torch
 
@@ -30,6 +32,35 @@ _LIBRARY.define("find_main_gap(Tensor x, float threshold) -> Tensor")
 _LIBRARY.define("find_gaps(Tensor x, float threshold, int min_len, int max_runs) -> (Tensor, Tensor)")
 _LIBRARY.define("linear_interp(Tensor x, float threshold) -> (Tensor, Tensor)")
 _LIBRARY.define("blend_boundaries(Tensor raw, Tensor restored, int gap_start, int gap_end, int blend_len) -> Tensor")
+
+
+# One handle per device owns shared scratch, pinned staging and the cached tables, and ctypes releases the GIL during a call:
+# two Python threads entering the library on the same device would share (and could free) that scratch.  Every op therefore
+# takes the device's lock around its C call.  Work of one device is also stream-ordered on ONE stream at a time: callers that
+# switch CUDA streams between ops must order those streams themselves (documented in include/ainmf.h and INTEGRATION.md).
+_locks: dict[int, threading.RLock] = {}
+_locks_guard = threading.Lock()
+
+
+def _lock(dev: int) -> threading.RLock:
+    with _locks_guard:
+        lk = _locks.get(dev)
+        if lk is None:
+            lk = _locks[dev] = threading.RLock()
+        return lk
+
+
+def _serialised(fn):
+    """Run `fn` holding the lock of the device of its first tensor argument."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        if t is None or not t.is_cuda:
+            return fn(*args, **kw)
+        dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        with _lock(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _dev(t: torch.Tensor) -> int:
@@ -259,6 +290,7 @@ def _blend_boundaries(raw, restored, gap_start, gap_end, blend_len):
     return out
 
 
+@_serialised
 def apply_gaps_(x, starts, lens):
     """In place: x[b, s:s+l] = 0 for the gap lists starts/lens [B, G] (int64, device) -- the zeroing step of the fixture
     producers (generate_part1_data.py:44-46, generate_part2_data.py:36-43)."""
@@ -304,6 +336,7 @@ def set_window(n_fft, window=None, device=None):
         _lib.check(L.ainmf_set_window(_lib.handle(dev), int(n_fft), ptr), dev)
 
 
+@_serialised
 def snr_db(ref, est, begin=0, end=None):
     """10 log10(sum ref^2 / (sum (ref - est)^2 + 1e-10)) over [begin, end) (main4_NMF.py:99-110); returns a Python float."""
     ref, est = _f32(ref, "ref"), _f32(est, "est")
@@ -320,11 +353,11 @@ def snr_db(ref, est, begin=0, end=None):
 
 for _name, _fn in (("find_main_gap", _find_main_gap), ("find_gaps", _find_gaps), ("linear_interp", _linear_interp),
                    ("blend_boundaries", _blend_boundaries)):
-    _LIBRARY.impl(_name, _fn, "CUDA")
+    _LIBRARY.impl(_name, _serialised(_fn), "CUDA")
 
 for _name, _fn in (("stft", _stft), ("gap_mask", _gap_mask), ("nmf_fit", _nmf_fit), ("istft", _istft),
                    ("nmf_inpaint", _nmf_inpaint), ("load_pcm16", _load_pcm16), ("store_pcm16", _store_pcm16)):
-    _LIBRARY.impl(_name, _fn, "CUDA")
+    _LIBRARY.impl(_name, _serialised(_fn), "CUDA")
 
 stft = torch.ops.ainmf.stft
 gap_mask = torch.ops.ainmf.gap_mask

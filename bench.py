@@ -347,7 +347,7 @@ KERNEL_NAMES = {"h_step_tc": "h_step_ts_kernel (X^T.W contraction on tcgen05 + H
 NCU_NAMES = {"h_step_tc": "h_step_ts_kernel", "xht_gram_tc": "xht_ts_kernel", "w_side_fused": "w_side_kernel"}
 
 
-def roofline_object(kern_ms, n_it, F, T, K, units, workload, note_iteration):
+def roofline_object(kern_ms, n_it, F, T, K, units, workload, note_iteration, traffic_units=None):
     """The contract's roofline object for the dominant kernel + the same accounting per kernel and for the whole iteration.
     units = spectrograms one launch processes (clips; 1 for the long signal, whose T is this rank's slice)."""
     peak, peak_src = peaks()
@@ -366,8 +366,9 @@ def roofline_object(kern_ms, n_it, F, T, K, units, workload, note_iteration):
     traffic, tfile = None, None
     tj = newest_traffic(workload)
     if tj and NCU_NAMES.get(dom) in tj.get("dram_bytes_per_launch", {}):
-        n_units = tj.get("units") or tj.get("clips")
-        traffic = tj["dram_bytes_per_launch"][NCU_NAMES[dom]] / n_units * units if n_units else None
+        n_units = tj.get("units") or tj.get("clips")       # clips (c4) or frames (c5) of the captured launch
+        now = traffic_units if traffic_units is not None else units
+        traffic = tj["dram_bytes_per_launch"][NCU_NAMES[dom]] / n_units * now if n_units else None
         tfile = tj["file"]
     return {"bound": "hbm", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": dom_ach, "peak": peak, "unit": "GB/s",
             "frac": dom_ach / peak, "traffic": traffic, "traffic_source": tfile, "peak_source": peak_src,
@@ -671,7 +672,7 @@ def leg_c5(ctx, steps, warmup, seconds=0.0, cpu_baseline=True, clocks=False):
                 "d2h_bytes_per_step": int(y.numel() * 4), "ms_per_step": e2e_ms / steps},
         "gpu_launches": int(launches), "clocks": clk,
         "roofline": roofline_object(kern_ms, n_it, F, Tl, K, 1, "c5",
-                                    "whole CD iteration on this rank (its frame slice; the W side is replicated, not sharded)"),
+                                    "whole CD iteration on this rank (its frame slice; the W side is replicated, not sharded)", traffic_units=Tl),
         "cpu_baseline": None, "parity": None,
     }
     del xh, yh, y, src

@@ -14,6 +14,10 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated;
  *   - return value: 0 on success, negative ainmf_status otherwise; text via ainmf_last_error();
  *   - no CPU fallback exists: without a CUDA device ainmf_create fails;
+ *   - threads and streams: a handle owns scratch memory, pinned staging, cached FFT / window / N(0,1) tables and the
+ *     pipeline streams of ainmf_inpaint_host, none of it locked.  Calls on ONE handle must not overlap in time (serialise
+ *     them, or give each thread its own handle), and consecutive calls on one handle should use one stream -- a caller
+ *     that changes streams between calls must order those streams itself, because scratch is reused from call to call;
  *   - layouts are the reference's: spectrogram-shaped outputs are (F, T) row-major exactly like the
  *     arrays `signal.stft` returns and `NMF` consumes ("W" is (F, K), "H" is (K, T)), EXCEPT the *_tf
  *     entry points, which use the library's internal frame-major [T][ldf] layout and avoid transposes.

@@ -1,11 +1,17 @@
 #!/usr/bin/env python
 """Turn the raw ncu outputs of profiles/run_profiles.sh (in gpurun_out/) into the tracked summaries under profiles/.
 
-    python profiles/summarize.py r01c        # reads gpurun_out/launches_r01c.csv, gpurun_out/prof_r01c.ncu-rep
+    python profiles/summarize.py r02            # c4: gpurun_out/launches_r02.csv, gpurun_out/prof_r02.ncu-rep
+    python profiles/summarize.py c5_r02 c5 51680   # c5 capture on a 600 s prefix: workload name and frames per launch
+
+Writes <tag>_launches.csv (per-kernel totals and shares), <tag>_ncu_full.csv (selected metrics of the captured launches)
+and <tag>_traffic.json (dram bytes per launch, what bench.py puts into roofline.traffic, scaled by units).
 """
 import csv, collections, json, os, subprocess, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+workload = sys.argv[2] if len(sys.argv) > 2 else "c4"
+units = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
@@ -35,6 +41,10 @@ keep = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.sum", "sm__inst_executed_pipe_tmem.sum", "sm__inst_executed_pipe_tc.sum",
+        "smsp__inst_executed_pipe_uniform.sum", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__waves_per_multiprocessor",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
 idx = [next((i for i, x in enumerate(h) if x == k or x.endswith("." + k)), None) for k in keep]
@@ -46,3 +56,23 @@ with open(os.path.join(P, f"{tag}_ncu_full.csv"), "w") as f:
         w.writerow([r[i] if i is not None else "" for i in idx])
 print(open(os.path.join(P, f"{tag}_launches.csv")).read())
 print(open(os.path.join(P, f"{tag}_ncu_full.csv")).read())
+
+# ---- dram traffic per launch (bench.py: roofline.traffic) -------------------------------------------------------
+ki = h.index("Kernel Name")
+ri = next(i for i, x in enumerate(h) if x.endswith("dram__bytes_read.sum"))
+wi = next(i for i, x in enumerate(h) if x.endswith("dram__bytes_write.sum"))
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+traffic = {}
+for r in rr[2:]:
+    name = r[ki].split("<")[0].split("(")[0].replace("void ", "").replace("ainmf::", "")
+    traffic[name] = to_bytes(r[ri], u[ri]) + to_bytes(r[wi], u[wi])
+json.dump({"source": f"profiles/{tag}_ncu_full.csv (ncu --set full, one launch of each kernel)", "workload": workload, "units": units,
+           "unit_is": "clips per launch" if workload != "c5" else "frames per launch", "dram_bytes_per_launch": traffic},
+          open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
+print(open(os.path.join(P, f"{tag}_traffic.json")).read())
+# tcgen05-related counters the capture holds (names vary by ncu version): printed so that they can be cited
+for i, x in enumerate(h):
+    if any(s_ in x for s_ in ("tensor", "_tc", "tmem", "uniform")):
+        print(x, [r[i] for r in rr[2:]])
