@@ -14,7 +14,7 @@ EXPORTS = [
     "ainmf_comm_unique_id", "ainmf_comm_init", "ainmf_shard_plan", "ainmf_sharded_workspace_bytes",
     "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile", "ainmf_comm_set_callbacks",
     "ainmf_find_main_gap", "ainmf_find_gaps", "ainmf_linear_interp", "ainmf_blend_boundaries", "ainmf_snr_db", "ainmf_apply_gaps",
-    "ainmf_set_window", "ainmf_standard_normal",
+    "ainmf_set_window", "ainmf_standard_normal", "ainmf_comm_transport",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
@@ -63,6 +63,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "ainmf_standard_normal": (C.c_int, [vp, C.c_uint32, i64, vp, vp]),
         "ainmf_comm_unique_id": (C.c_int, [vp]),
         "ainmf_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "ainmf_comm_transport": (C.c_int, [vp]),
         "ainmf_comm_set_callbacks": (C.c_int, [vp, i32, i32, ALLREDUCE_FN, SENDRECV_FN, vp]),
         "ainmf_shard_plan": (C.c_int, [i64, i32, i32, i32, i32, P(i32), P(i32), P(i64), P(i64), P(i64), P(i64)]),
         "ainmf_sharded_workspace_bytes": (sz, [vp, P(Params)]),

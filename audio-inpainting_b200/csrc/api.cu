@@ -813,8 +813,16 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     long long chunk = (long long)(max_device_bytes / per_clip);
     if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
     if (chunk > 512) chunk = 512;
-    if (p->batch >= 256 && chunk > (p->batch + 1) / 2) chunk = (p->batch + 1) / 2;
     if (chunk > p->batch) chunk = p->batch;
+    // The persistent kernels hand out (clip, tile) items to one CTA per SM, every item the same size: a chunk of n_sm clips
+    // (or a multiple) fills every round of every kernel exactly, so splitting a batch into such chunks costs no extra
+    // rounds, and with ~4 chunks only the first quarter's copy-in and the last (short) chunk's copy-out stay exposed.
+    if (p->batch >= 2 * h->n_sm) {
+        long long m = (p->batch / 4) / h->n_sm;
+        if (m < 1) m = 1;
+        if (m * h->n_sm < chunk) chunk = m * h->n_sm;
+        else if (chunk >= h->n_sm) chunk = chunk / h->n_sm * h->n_sm;
+    }
     ainmf_params cp = *p;
     cp.batch = (int32_t)chunk;
     const size_t ws = ainmf_workspace_bytes(h, &cp);

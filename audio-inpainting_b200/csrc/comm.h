@@ -30,6 +30,13 @@ int comm_rank(const Comm* c);
 int comm_size(const Comm* c);
 // in-place all-reduce of `count` elements on `s`
 int comm_allreduce(Comm* c, void* buf, size_t count, int dtype, int op, cudaStream_t s, char* err, size_t errlen);
+// Peer mailboxes (NCCL back end only): every rank maps a slot buffer of every other rank (CUDA IPC over NVLink) so that
+// the per-iteration all-reduce becomes two small kernels of our own -- push this rank's contribution into its slot on
+// every rank, then sum the slots in rank order -- instead of a library collective between the kernels.  Collective:
+// every rank calls it with the same capacity.  After it, comm_allreduce routes float32/float64 sums of up to
+// `cap_bytes` through the mailboxes; AINMF_PEER_EXCHANGE=0 keeps everything on ncclAllReduce.
+int comm_peer_setup(Comm* c, size_t cap_bytes, cudaStream_t s, char* err, size_t errlen);
+int comm_peer_active(const Comm* c);
 // simultaneous send to `send_peer` and receive from `recv_peer` (either may be -1 = none), float payloads
 int comm_sendrecv(Comm* c, const void* sendbuf, int send_peer, void* recvbuf, int recv_peer, size_t n_floats,
                   cudaStream_t s, char* err, size_t errlen);

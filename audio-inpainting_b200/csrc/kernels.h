@@ -217,6 +217,8 @@ cudaError_t nmf_mu_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaS
 // the same iteration in pieces, so that a collective can be placed between them (time-sharded mode):
 // PARTIALS: HHt and X.Ht of the local frames; UPDATE: W sweep, WtW, fused X^T.W + H sweep; STOP: the stop rule
 cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s);
+// nmf_wside.cu: the W half-step (w_side_kernel + w_finish_kernel); S = number of X.Ht partial buffers to sum
+cudaError_t launch_w_side(const NmfProblem& p, const NmfWork& wk, int S, cudaStream_t s);
 cudaError_t launch_set_err(ClipState* st, int B, const double* err_sq, cudaStream_t s);
 // ---- nmf_small.cu: a small spectrogram's whole fit -- and main4_NMF.py's chain of n_outer refits -- in one launch, one CTA
 // per clip, everything in shared memory (seeded initial factors).  bad: frames replaced by (W H)

@@ -236,330 +236,6 @@ xht_kernel(const float* __restrict__ Xt, long long x_stride, int ldf, int F, int
 }
 
 // =====================================================================================================
-// W side of the iteration in one kernel; grid = (ceil(F/ROWS), B), 128 threads, a group of L lanes per row of W:
-//   B = sum_s partial[s] (fixed order);  g = W.G - B accumulated as rank-1 updates (rows of zeros are skipped);
-//   W <- sweep(W, G = HHt, B) in the incremental-gradient form: the whole gradient lives in registers, a coordinate
-//     step costs KP FMAs per row instead of a dot product, shuffles and the update logic on every lane;
-//   the new rows stay in shared memory and feed: the store of W; (tensor-core path) W^T and its bf16 cross operand
-//     for the H step's contraction (see tc::cross_pack8); the block's share of W^T W (register-tiled FFMA).
-//   w_finish_kernel then sums the Gram partials in block order (deterministic) and (tensor-core path) derives the
-//   H step's sweep operands from them (g_prep_block).
-// $SP/sklearn/decomposition/_nmf.py:379-396 (X.Ht, HHt -> W sweep), then :379-380 for the H half (W^T W).
-// =====================================================================================================
-template <int KP, int L_, int ROWS_> struct WSideCfg {
-    static constexpr int L = L_;                           // lanes per row: 1 for big batches (fewest instructions), up to 8 when
-    static constexpr int SL = KP / L;                      // few rows must fill the machine (shorter serial chain per lane)
-    static constexpr int ROWS = ROWS_;                     // rows per block: 128, or 32 (with the most lanes) for a single clip
-    static constexpr int THREADS = ROWS * L;
-    static_assert(SL >= 4 && SL <= 64 && THREADS / 16 <= KP && THREADS >= 128, "lanes per row");
-    static constexpr int GP = KP + 4 * L;                  // Gram row pitch (load_gram_padded<KP, L>)
-    static constexpr int AP = KP + 4;                      // row pitch of the W tile (16-byte aligned rows)
-    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)KP * GP + KP + (size_t)ROWS * AP);
-};
-struct WSideTc {                      // outputs for the tensor-core H step; all null on the FFMA path
-    float* Wt; float* WtX; long long wt_stride; int ldw;
-    float* GX; float* blobs; float* scal;
-    // good-first frame order: the bad frames' share of X.Ht is fill (x) hbad, and the H step needs v = fill^T.W
-    const float* fill; long long fill_stride; const float* hbad; float* vpartial; float* vfill;
-};
-template <int KP, int LANES, int NROWS>
-__global__ void __launch_bounds__(NROWS * LANES)
-w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
-              const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
-              float* __restrict__ gram_partial /*[B][gridDim.x][KP*KP]*/, WSideTc tc_out, const ClipState* __restrict__ st,
-              float* __restrict__ pg_out /*[B][F][KP] or null*/) {
-    using Cfg = WSideCfg<KP, LANES, NROWS>;
-    constexpr int L = Cfg::L, SL = Cfg::SL, ROWS = Cfg::ROWS, GP = Cfg::GP, AP = Cfg::AP;
-    AINMF_DYN_SMEM(smem_raw);
-    float* sG = reinterpret_cast<float*>(smem_raw);       // [KP][GP]
-    float* sInv = sG + KP * GP;                           // [KP]
-    float* sA = sInv + KP;                                // [ROWS][AP]
-    __shared__ float s_red[32];
-    const int b = blockIdx.y, P = gridDim.x;
-    if (st[b].done) return;
-    const float* Gb = G + (long long)b * KP * KP;
-    load_gram_padded<KP, L>(sG, Gb);
-    for (int t = threadIdx.x; t < KP; t += blockDim.x) { const float d = Gb[t * KP + t]; sInv[t] = (d != 0.f) ? 1.0f / d : 0.f; }
-    const int f0 = blockIdx.x * ROWS;
-    float vsum = 0.f;
-    if constexpr (L == 1) {
-        // One thread per row, the reference's own formulation (_cdnmf_fast.pyx:8-38): the gradient of coordinate t is a dot
-        // product of the row (registers) with row t of G (shared, packed FFMA2, four chains); nothing is updated
-        // incrementally -- K^2 FMAs per row instead of the 2 K^2 of the rank-1 form.  -B waits in the row's slot of the
-        // shared tile, which receives the new row afterwards.
-        const int r = threadIdx.x;
-        const int f = f0 + r;
-        const bool valid = f < F;
-        float* ar = sA + r * AP;
-        {
-            float4 nb[KP / 4];
-#pragma unroll
-            for (int q = 0; q < KP / 4; ++q) nb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                for (int s = 0; s < S; ++s) {              // fixed order -> deterministic
-                    const float* pr = partial + ((((long long)b * S + s) * F) + f) * KP;
-#pragma unroll
-                    for (int q = 0; q < KP / 4; ++q) {
-                        const float4 v = *reinterpret_cast<const float4*>(pr + 4 * q);
-                        nb[q].x -= v.x; nb[q].y -= v.y; nb[q].z -= v.z; nb[q].w -= v.w;
-                    }
-                }
-            }
-            if (valid && tc_out.hbad) {                    // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
-                const float fl = tc_out.fill[(long long)b * tc_out.fill_stride + f];
-                const float4* hb = reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP);
-#pragma unroll
-                for (int q = 0; q < KP / 4; ++q) {
-                    const float4 v = hb[q];
-                    nb[q].x = fmaf(-fl, v.x, nb[q].x); nb[q].y = fmaf(-fl, v.y, nb[q].y);
-                    nb[q].z = fmaf(-fl, v.z, nb[q].z); nb[q].w = fmaf(-fl, v.w, nb[q].w);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < KP / 4; ++q) *reinterpret_cast<float4*>(ar + 4 * q) = nb[q];
-        }
-        float a[KP];
-#pragma unroll
-        for (int q = 0; q < KP; ++q) a[q] = 0.f;
-        if (valid) {
-            const float* wr = W + (long long)b * w_stride + (long long)f * KP;
-#pragma unroll
-            for (int q = 0; q < KP; q += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(wr + q);
-                a[q] = v.x; a[q + 1] = v.y; a[q + 2] = v.z; a[q + 3] = v.w;
-            }
-        }
-        __syncthreads();
-        // F = 2^m + 1 leaves the last block of a clip with one row: warps without a valid row skip the sweep
-        if (__ballot_sync(0xffffffffu, valid) != 0u) {
-#pragma unroll
-        for (int t = 0; t < KP; ++t) {
-            const float* gr = sG + t * GP;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-            for (int q = 0; q < KP; q += 4) {
-                const float4 gv = *reinterpret_cast<const float4*>(gr + q);
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
-                const float2 p0 = __ffma2_rn(make_float2(a[q], a[q + 1]), make_float2(gv.x, gv.y), make_float2(d0, d1));
-                const float2 p1 = __ffma2_rn(make_float2(a[q + 2], a[q + 3]), make_float2(gv.z, gv.w), make_float2(d2, d3));
-                d0 = p0.x; d1 = p0.y; d2 = p1.x; d3 = p1.y;
-#else
-                d0 = fmaf(a[q], gv.x, d0); d1 = fmaf(a[q + 1], gv.y, d1);
-                d2 = fmaf(a[q + 2], gv.z, d2); d3 = fmaf(a[q + 3], gv.w, d3);
-#endif
-            }
-            const float grad = ((d0 + d1) + (d2 + d3)) + ar[t];
-            const float inv = sInv[t];
-            const float aq = a[t];
-            const float pg = (aq == 0.f) ? fminf(0.f, grad) : grad;
-            vsum += valid ? fabsf(pg) : 0.f;
-            if (pg_out && valid) pg_out[((long long)b * F + f) * KP + t] = fabsf(pg);
-            if (valid && inv != 0.f) a[t] = fmaxf(fmaf(-grad, inv, aq), 0.f);
-        }
-        }
-#pragma unroll
-        for (int q = 0; q < KP; q += 4) *reinterpret_cast<float4*>(ar + q) = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
-    } else {
-    const int l = threadIdx.x % L, r = threadIdx.x / L;
-    const int f = f0 + r;
-    const bool valid = f < F;
-    float* ar = sA + r * AP;
-    float g[SL];
-#pragma unroll
-    for (int q = 0; q < SL; ++q) g[q] = 0.f;
-    if (valid) {
-        const float* wr = W + (long long)b * w_stride + (long long)f * KP + l * SL;
-#pragma unroll
-        for (int q = 0; q < SL; q += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(wr + q);
-            ar[l * SL + q] = v.x; ar[l * SL + q + 1] = v.y; ar[l * SL + q + 2] = v.z; ar[l * SL + q + 3] = v.w;
-        }
-        for (int s = 0; s < S; ++s) {                      // fixed order -> deterministic
-            const float* pr = partial + ((((long long)b * S + s) * F) + f) * KP + l * SL;
-#pragma unroll
-            for (int q = 0; q < SL; q += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(pr + q);
-                g[q] -= v.x; g[q + 1] -= v.y; g[q + 2] -= v.z; g[q + 3] -= v.w;
-            }
-        }
-        if (tc_out.hbad) {                                 // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
-            const float fl = tc_out.fill[(long long)b * tc_out.fill_stride + f];
-            const float* hb = tc_out.hbad + (long long)b * KP + l * SL;
-#pragma unroll
-            for (int q = 0; q < SL; ++q) g[q] = fmaf(-fl, hb[q], g[q]);
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < SL; ++q) ar[l * SL + q] = 0.f;
-    }
-    __syncthreads();
-    const float* gl = sG + l * (SL + 4);
-    auto rank1 = [&](float c, int t) {                     // g[:] += c * G[t][this lane's slice]
-        const float* gr = gl + t * GP;
-#pragma unroll
-        for (int q = 0; q < SL; q += 4) {
-            const float4 gv = *reinterpret_cast<const float4*>(gr + q);
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
-            const float2 cc = make_float2(c, c);
-            const float2 lo2 = __ffma2_rn(cc, make_float2(gv.x, gv.y), make_float2(g[q], g[q + 1]));
-            const float2 hi2 = __ffma2_rn(cc, make_float2(gv.z, gv.w), make_float2(g[q + 2], g[q + 3]));
-            g[q] = lo2.x; g[q + 1] = lo2.y; g[q + 2] = hi2.x; g[q + 3] = hi2.y;
-#else
-            g[q] = fmaf(c, gv.x, g[q]); g[q + 1] = fmaf(c, gv.y, g[q + 1]);
-            g[q + 2] = fmaf(c, gv.z, g[q + 2]); g[q + 3] = fmaf(c, gv.w, g[q + 3]);
-#endif
-        }
-    };
-    // gradient at the old W:  g = W.G - B  (G symmetric: row t of G scaled by W[row][t])
-#pragma unroll 4
-    for (int t = 0; t < KP; ++t) {
-        const float c = ar[t];
-        if (__ballot_sync(0xffffffffu, c != 0.f) == 0u) continue;       // warp-uniform
-        rank1(c, t);
-    }
-    // the sweep (reference order t = 0..KP-1); the lane that owns coordinate t decides, everybody applies the delta
-#pragma unroll
-    for (int t = 0; t < KP; ++t) {
-        const int o = t / SL, q = t % SL;
-        const float inv = sInv[t];
-        const float aq = ar[t];
-        const float grad = g[q];
-        const float pg = (aq == 0.f) ? fminf(0.f, grad) : grad;
-        const float an = fmaxf(fmaf(-grad, inv, aq), 0.f);
-        const bool own = (l == o) && valid;
-        const bool upd = own && (inv != 0.f);
-        vsum += own ? fabsf(pg) : 0.f;
-        if (pg_out && own) pg_out[((long long)b * F + f) * KP + t] = fabsf(pg);
-        float d = upd ? an - aq : 0.f;
-        if (upd) ar[t] = an;
-        if (L > 1) d = __shfl_sync(0xffffffffu, d, o, L);
-        if (__ballot_sync(0xffffffffu, d != 0.f) == 0u) continue;       // warp-uniform
-        rank1(d, t);
-    }
-    }
-    __syncthreads();
-
-    // ---- the new rows: W ------------------------------------------------------------------------------------------
-    const int rows_here = min(ROWS, F - f0);
-    float* Wb = W + (long long)b * w_stride + (long long)f0 * KP;
-    for (int i = threadIdx.x; i < rows_here * KP / 4; i += blockDim.x)
-        *reinterpret_cast<float4*>(Wb + 4 * i) = *reinterpret_cast<const float4*>(sA + ((4 * i) / KP) * AP + ((4 * i) % KP));
-#ifndef AINMF_EMU
-    if (tc_out.Wt) {
-        // Wt[k][f] = W[f][k] (tf32 main-term operand) and WtX, the bf16 cross operand with the same footprint: per group of
-        // 8 consecutive f, words 0-3 = pairs of bf16(w), words 4-7 = pairs of bf16(w - trunc_tf32(w))
-        float* Wt = tc_out.Wt + (long long)b * tc_out.wt_stride;
-        float* WtX = tc_out.WtX + (long long)b * tc_out.wt_stride;
-        for (int i = threadIdx.x; i < KP * ROWS; i += blockDim.x) {
-            const int k = i / ROWS, rr = i % ROWS, ff = f0 + rr;
-            if (ff >= tc_out.ldw) continue;
-            Wt[(long long)k * tc_out.ldw + ff] = sA[rr * AP + k];
-            const int g8 = rr & ~7, wd = rr & 7, e = 2 * (wd & 3);
-            const float v0 = sA[(g8 + e) * AP + k], v1 = sA[(g8 + e + 1) * AP + k];
-            uint32_t word;
-            if (wd < 4) word = tc::pack_bf16x2(v0, v1);
-            else { float h, l0, l1; tc::split_tf32(v0, h, l0); tc::split_tf32(v1, h, l1); word = tc::pack_bf16x2(l0, l1); }
-            WtX[(long long)k * tc_out.ldw + ff] = __uint_as_float(word);
-        }
-    }
-#endif
-    if (tc_out.vpartial) {
-        for (int k = threadIdx.x; k < KP; k += blockDim.x) {
-            float acc = 0.f;
-            for (int rr = 0; rr < rows_here; ++rr) acc = fmaf(tc_out.fill[(long long)b * tc_out.fill_stride + f0 + rr], sA[rr * AP + k], acc);
-            tc_out.vpartial[((long long)b * P + blockIdx.x) * KP + k] = acc;
-        }
-    }
-    // ---- this block's share of W^T W: thread (ty, tx) of a (THREADS/16) x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
-    {
-        constexpr int TY = Cfg::THREADS / 16, TI = KP / TY, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
-        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-        float* out = gram_partial + ((long long)b * P + blockIdx.x) * (KP * KP);
-#pragma unroll 1
-        for (int pass = 0; pass < PASSES; ++pass) {
-            float acc[TI][TJ];
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
-            const int c0 = pass * 16 * TJ + tx * TJ;
-#pragma unroll 2
-            for (int rr = 0; rr < rows_here; ++rr) {        // rows past the clip's last one are zero
-                const float* row = sA + rr * AP;
-                float fi[TI], fj[TJ];
-                if constexpr (TI % 4 == 0) {
-#pragma unroll
-                    for (int i = 0; i < TI; i += 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(row + ty * TI + i);
-                        fi[i] = v.x; fi[i + 1] = v.y; fi[i + 2] = v.z; fi[i + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < TI; ++i) fi[i] = row[ty * TI + i];
-                }
-                if constexpr (TJ == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + c0);
-                    fj[0] = v.x; fj[1] = v.y; fj[2] = v.z; fj[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) fj[j] = row[c0 + j];
-                }
-#pragma unroll
-                for (int i = 0; i < TI; ++i) {
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
-#pragma unroll
-                    for (int j = 0; j < TJ; j += 2) {
-                        const float2 r2 = __ffma2_rn(make_float2(fi[i], fi[i]), make_float2(fj[j], fj[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
-                        acc[i][j] = r2.x; acc[i][j + 1] = r2.y;
-                    }
-#else
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) acc[i][j] = fmaf(fi[i], fj[j], acc[i][j]);
-#endif
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) out[(ty * TI + i) * KP + c0 + j] = acc[i][j];
-        }
-    }
-    const float tot = block_sum(vsum, s_red);
-    if (threadIdx.x == 0) viol[(long long)b * P + blockIdx.x] = tot;
-
-}
-
-// W^T W = sum of the W-side kernel's partials in block order (deterministic), 8 rows per block, and (tensor-core path) the
-// H step's operands that derive from those 8 rows (g_prep_block); grid = (KP/8, B)
-__global__ void __launch_bounds__(kThreads)
-w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P, int KP, float* __restrict__ WtW, WSideTc tc_out,
-                const ClipState* __restrict__ st) {
-    const int b = blockIdx.y, blk = blockIdx.x;
-    if (st[b].done) return;
-    const float* pb = gram_partial + (long long)b * P * (KP * KP) + 8 * blk * KP;
-    float* Go = WtW + (long long)b * (KP * KP);
-    for (int e = threadIdx.x; e < 8 * KP; e += blockDim.x) {
-        float sum = 0.f;
-        for (int q = 0; q < P; ++q) sum += pb[(long long)q * (KP * KP) + e];
-        Go[8 * blk * KP + e] = sum;
-    }
-#ifndef AINMF_EMU
-    if (tc_out.blobs) {
-        __syncthreads();                                 // the rows just written are read back by other threads of the block
-        g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
-                     tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
-        if (threadIdx.x < 8) {                           // v[8blk + j] = fill^T.W: the X^T.W row of every bad frame
-            if (tc_out.vpartial) {
-                float v = 0.f;
-                for (int q = 0; q < P; ++q) v += tc_out.vpartial[((long long)b * P + q) * KP + 8 * blk + threadIdx.x];
-                tc_out.vfill[(long long)b * KP + 8 * blk + threadIdx.x] = v;
-            }
-        }
-    }
-#endif
-}
-
-// =====================================================================================================
 // h step: XtW tile = Xt[tile] W ; Ht[tile] <- sweep(Ht[tile], WtW, XtW tile); grid = (ceil(T/BM), B)
 // =====================================================================================================
 template <int KP, int BM> struct HStepCfg {
@@ -1033,34 +709,9 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
         }
     }
     if (phases & NMF_PHASE_UPDATE) {
-        {
-            WSideTc tco{nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
-            if (wk.use_tc) tco = WSideTc{wk.tc_Wt, wk.tc_WtLo, (long long)KP * p.ldf, p.ldf, wk.tc_GLo, wk.tc_blobs, wk.tc_scal,
-                                         p.t_good ? p.fill : nullptr, p.fill_stride, p.t_good ? wk.tc_hbad : nullptr,
-                                         p.t_good ? wk.tc_vpartial : nullptr, wk.tc_vfill};
-            prof_begin(PROF_W_SWEEP, s);
-            auto launch = [&](auto cfg) -> cudaError_t {
-                using WC = decltype(cfg);
-                auto kern = w_side_kernel<KP, WC::L, WC::ROWS>;
-                cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::smem_bytes);
-                if (e2 != cudaSuccess) return e2;
-                AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
-                             wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, wk.gram_partial,
-                             tco, p.state, wk.exact_viol ? wk.pgW : nullptr);
-                return cudaGetLastError();
-            };
-            constexpr int LMIN = (KP == 128) ? 2 : 1, LMAX = (KP == 32) ? 4 : 8;
-            int lanes = wk.w_lanes < LMIN ? LMIN : (wk.w_lanes > LMAX ? LMAX : wk.w_lanes);
-            if (wk.w_rows == 32) e = launch(WSideCfg<KP, LMAX, 32>{});
-            else if (lanes >= 8) { if constexpr (LMAX >= 8) e = launch(WSideCfg<KP, 8, 128>{}); }
-            else if (lanes >= 4) e = launch(WSideCfg<KP, 4, 128>{});
-            else if (lanes >= 2) e = launch(WSideCfg<KP, 2, 128>{});
-            else { if constexpr (LMIN <= 1) e = launch(WSideCfg<KP, 1, 128>{}); }
-            if (e != cudaSuccess) return e;
-            AINMF_LAUNCH(w_finish_kernel, dim3(KP / 8, p.B), dim3(kThreads), 0, s, wk.gram_partial, wk.nW, KP, wk.WtW, tco, p.state);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            prof_end(PROF_W_SWEEP, s);
-        }
+        prof_begin(PROF_W_SWEEP, s);
+        if ((e = launch_w_side(p, wk, S, s)) != cudaSuccess) return e;
+        prof_end(PROF_W_SWEEP, s);
         // H half-step (W^T W came out of the W-side kernel)
         prof_begin(PROF_H_STEP, s);
         if (wk.use_tc) e = nmf_tc_hstep(p, wk, s);
@@ -1295,6 +946,7 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
         while (lanes < 8 && blocks * 4 * lanes < 8LL * n_sm) lanes *= 2;
         wk->w_lanes = lanes;
         if (lanes == 8 && blocks * 2 < n_sm) { wk->w_rows = 32; wk->nW = ceil_div(F, 32); }
+        if (lanes == 1 && KP <= 64) { wk->w_rows = 256; wk->nW = ceil_div(F, 256); }     // two rows per thread (nmf_wside.cu)
     }
     const int f_tiles = ceil_div(F, 128);
     long long splits = want / ((long long)B * f_tiles);

@@ -671,6 +671,9 @@ def leg_c5(ctx, steps, warmup, seconds=0.0, cpu_baseline=True, clocks=False):
         "e2e": {"value": audio_s * steps / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(src.numel() * 4),
                 "d2h_bytes_per_step": int(y.numel() * 4), "ms_per_step": e2e_ms / steps},
         "gpu_launches": int(launches), "clocks": clk,
+        "transport": {0: "single rank", 1: "ncclAllReduce between the kernels of an iteration",
+                      2: "peer mailboxes over NVLink (CUDA IPC): push kernel + ordered slot sum, no library collective "
+                         "inside the iteration"}[int(L.ainmf_comm_transport(h))],
         "roofline": roofline_object(kern_ms, n_it, F, Tl, K, 1, "c5",
                                     "whole CD iteration on this rank (its frame slice; the W side is replicated, not sharded)", traffic_units=Tl),
         "cpu_baseline": None, "parity": None,

@@ -189,6 +189,12 @@ int ainmf_profile(ainmf_handle h, int32_t enable, double* ms_out, int64_t* count
  * ainmf_comm_unique_id on rank 0 and distributed by the caller (torch.distributed broadcast). */
 int ainmf_comm_unique_id(uint8_t id_out[128]);
 int ainmf_comm_init(ainmf_handle h, const uint8_t unique_id[128], int32_t rank, int32_t nranks);
+/* Which transport carries the per-iteration sums of ainmf_inpaint_sharded: 0 = no group / one rank, 1 = ncclAllReduce
+ * or the caller's callbacks, 2 = peer mailboxes (every rank writes its F*K + K*K partial sums straight into a slot on
+ * every other rank over NVLink -- CUDA IPC mappings made at the first sharded call -- and sums the slots in rank order
+ * in a kernel of its own; no library collective between the kernels of an iteration).  Mailboxes are the default with
+ * the NCCL group; AINMF_PEER_EXCHANGE=0 in the environment keeps ncclAllReduce. */
+int ainmf_comm_transport(ainmf_handle h);
 /* Alternative transport: the caller supplies the two collectives (used by the CPU test-suite over gloo).
  * dtype: 0 float32, 1 float64, 2 int32; op: 0 sum, 1 max; peers < 0 mean "none"; return 0 on success. */
 typedef int (*ainmf_allreduce_fn)(void* user, void* buf, size_t count, int dtype, int op, void* stream);

@@ -29,6 +29,8 @@ def main():
     tsi = TimeShardedInpainter(dev)
     pl = tsi.plan(N, 2048, 512)
     y, info = tsi.restore(x[pl["x_begin"]:pl["x_end"]].clone(), N, n_fft=2048, hop=512, rank=K, max_iter=40, tol=1e-4, seed=0)
+    transport = int(ainmf._lib.lib().ainmf_comm_transport(tsi.h))
+    want_transport = 1 if os.environ.get("AINMF_PEER_EXCHANGE") == "0" else 2
     parts = [None] * world
     dist.all_gather_object(parts, (pl["y_begin"], pl["y_end"], y.cpu().numpy(), int(info["n_bad"][0]), int(info["n_iter"][0]),
                                    float(info["err"][0])))
@@ -44,8 +46,8 @@ def main():
         snr = 10 * np.log10(num / (den + 1e-10))
         rel = abs(parts[0][5] - float(err[0])) / float(err[0])
         print(f"world {world}: N={N} K={K} n_bad {parts[0][3]} vs {int(nbs[0])}, n_iter {parts[0][4]} vs {int(nit[0])}, "
-              f"objective rel diff {rel:.2e}, stitched-vs-single SNR {snr:.1f} dB")
-        ok = parts[0][3] == int(nbs[0]) and parts[0][4] == int(nit[0]) and rel < 1e-4 and snr > 60
+              f"objective rel diff {rel:.2e}, stitched-vs-single SNR {snr:.1f} dB, transport {transport}")
+        ok = transport == want_transport and parts[0][3] == int(nbs[0]) and parts[0][4] == int(nit[0]) and rel < 1e-4 and snr > 60
         print("SHARDED_OK" if ok else "SHARDED_FAIL")
     dist.barrier()
     dist.destroy_process_group()

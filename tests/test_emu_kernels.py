@@ -60,6 +60,22 @@ def test_emu_nmf_fit(F, T, K, iters):
     assert rel_l2(W[0], Wo) < 1e-4 and rel_l2(H[0], Ho) < 1e-4
 
 
+@pytest.mark.parametrize("F,T,K,B,iters", [(129, 50, 40, 4, 3), (140, 36, 20, 8, 3)])
+def test_emu_nmf_fit_batch_one_thread_per_row_w_side(F, T, K, B, iters):
+    """A batch large enough (for the emulator's 4 SMs) that the W side takes its one-thread-per-row shape: the blocked
+    sweep (blocks of 8 coordinates, in-block corrections) must reproduce sklearn's sequential sweep; F = 129 leaves the
+    last block of every clip with a single row (as F = 513 does at the real sizes)."""
+    rng = np.random.default_rng(F + B)
+    X = np.abs(rng.standard_normal((B, F, T))).astype(np.float32)
+    X[1, :, 5:9] = 0.0                                     # a clip with zero columns: some coordinates hit the bound
+    W, H, err, nit = E.nmf_fit(X, K, max_iter=iters, tol=0.0, seed=42)
+    for b in range(B):
+        Wo, Ho, no, eo = libcalls.nmf_fit(X[b], K, seed=42, max_iter=iters, tol=0.0)
+        assert nit[b] == no
+        assert abs(err[b] - eo) < 1e-5 * eo
+        assert rel_l2(W[b], Wo) < 1e-4 and rel_l2(H[b], Ho) < 1e-4
+
+
 def test_emu_whole_path_and_edge_cases():
     rng = np.random.default_rng(2)
     N, n_fft, hop, K = 6000, 128, 32, 8
