@@ -168,8 +168,9 @@ struct TcMaps { TcMapBlob mapX, mapWt, mapWtLo, mapXs, mapHs, mapHmn, mapHk, map
 
 constexpr int kSweepScalars = 136;   // per block of 8 coordinates: G diagonal block 8x8, look-ahead block 8x8, 1/diag (8)
 
+constexpr int kWSideTail = 32;          // rows beyond ROWS that the last W-side block of a clip may take (one lane per row shape)
 struct NmfWork {
-    int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64, w_lanes = 1, w_rows = 128;
+    int h_bm = 64, nW = 0, nH = 0, xht_splits = 1, gram_max_blocks = 64, w_lanes = 1, w_rows = 128, finish_gpb = 1;
     // tensor-core path (tcgen05: tf32 main term + bf16 cross terms) for the two V-sized contractions; KP in {64,128}
     int use_tc = 0, tc_splits = 1, tc_fps = 0, tc_mtiles = 0;
     float *tc_Wt = nullptr, *tc_WtLo = nullptr;   // [B][KP][ldf]: W transposed (tf32 main-term operand), and its bf16 cross-term operand (tc::cross_pack8)

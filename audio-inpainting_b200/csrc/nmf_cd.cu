@@ -946,7 +946,16 @@ void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk) {
         while (lanes < 8 && blocks * 4 * lanes < 8LL * n_sm) lanes *= 2;
         wk->w_lanes = lanes;
         if (lanes == 8 && blocks * 2 < n_sm) { wk->w_rows = 32; wk->nW = ceil_div(F, 32); }
-        if (lanes == 1 && KP <= 64) { wk->w_rows = 256; wk->nW = ceil_div(F, 256); }     // two rows per thread (nmf_wside.cu)
+        if (lanes == 1 && KP <= 64) {                       // two rows per thread (nmf_wside.cu); a remainder of at most
+            wk->w_rows = 256;                               // kWSideTail rows (F = 2^m + 1) rides with the clip's last block
+            const int rem = F % 256;
+            wk->nW = (F > 256 && rem > 0 && rem <= kWSideTail) ? F / 256 : ceil_div(F, 256);
+        }
+    }
+    {   // w_finish_kernel: groups of 8 Gram rows per block -- as many as still leave two blocks per SM
+        int gpb = 1;
+        while (gpb * 2 <= KP / 8 && (long long)B * (KP / 8 / (gpb * 2)) >= want) gpb *= 2;
+        wk->finish_gpb = gpb;
     }
     const int f_tiles = ceil_div(F, 128);
     long long splits = want / ((long long)B * f_tiles);

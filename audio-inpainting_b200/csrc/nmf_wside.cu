@@ -33,9 +33,16 @@ template <int KP, int L_, int ROWS_> struct WSideCfg {
     static constexpr int RPT = (L == 1) ? 2 : 1;           // rows per thread: with one lane per row a thread sweeps two rows, so
     static constexpr int THREADS = ROWS * L / RPT;         // that every Gram value fetched from shared memory feeds two FFMA2
     static_assert(SL >= 4 && SL <= 64 && THREADS / 16 <= KP && THREADS >= 128, "lanes per row");
+    // F = 2^m + 1 would leave every clip a block with a single row, which holds an SM slot for the latency of a whole
+    // sweep: with one lane per row the last block of a clip takes up to TAIL rows beyond its ROWS, swept by one more warp
+    // (one row per lane) that runs next to the block's other warps
+    static constexpr int TAIL = (L == 1) ? kWSideTail : 0;
+    static constexpr int LAUNCH_THREADS = THREADS + TAIL;
+    static constexpr int TROWS = ROWS + TAIL;              // rows of the shared-memory tile (one more, all zero, when TAIL > 0:
+                                                           // the unused second row of the extra warp's lanes)
     static constexpr int GP = KP + 4 * L;                  // Gram row pitch (load_gram_padded<KP, L>)
     static constexpr int AP = KP + 4;                      // row pitch of the W tile (16-byte aligned rows)
-    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)KP * GP + KP + (size_t)ROWS * AP);
+    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)KP * GP + KP + (size_t)(TROWS + (TAIL ? 1 : 0)) * AP);
 };
 struct WSideTc {                      // outputs for the tensor-core H step; all null on the FFMA path
     float* Wt; float* WtX; long long wt_stride; int ldw;
@@ -44,7 +51,7 @@ struct WSideTc {                      // outputs for the tensor-core H step; all
     const float* fill; long long fill_stride; const float* hbad; float* vpartial; float* vfill;
 };
 template <int KP, int LANES, int NROWS>
-__global__ void __launch_bounds__(WSideCfg<KP, LANES, NROWS>::THREADS, (LANES == 1) ? 2 : 1)
+__global__ void __launch_bounds__(WSideCfg<KP, LANES, NROWS>::LAUNCH_THREADS, (LANES == 1) ? 2 : 1)
 w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __restrict__ G,
               const float* __restrict__ partial, int S, float* __restrict__ viol /*[B][gridDim.x]*/,
               float* __restrict__ gram_partial /*[B][gridDim.x][KP*KP]*/, WSideTc tc_out, const ClipState* __restrict__ st,
@@ -62,6 +69,8 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
     load_gram_padded<KP, L>(sG, Gb);
     for (int t = threadIdx.x; t < KP; t += blockDim.x) { const float d = Gb[t * KP + t]; sInv[t] = (d != 0.f) ? 1.0f / d : 0.f; }
     const int f0 = blockIdx.x * ROWS;
+    // rows of this block: ROWS, except that the clip's last block takes what is left (at most TROWS, see nmf_plan)
+    const int rows_here = ((int)blockIdx.x == P - 1) ? F - f0 : ROWS;
     float vsum = 0.f;
     if constexpr (L == 1) {
         // Big batches: the tile holds the rows of W, a thread sweeps rows r and r + ROWS/2.  The sweep is the reference's
@@ -73,50 +82,46 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         // FMAs per row.  Loops stay rolled (the row lives in shared memory, not in registers): ~400 instructions of code
         // instead of an unrolled 100 KB that no instruction cache holds.
         constexpr int HR = ROWS / 2;
-        const int rows_in = min(ROWS, F - f0);
         {
             const float4* Wg = reinterpret_cast<const float4*>(W + (long long)b * w_stride + (long long)f0 * KP);
-            for (int i = threadIdx.x; i < ROWS * KP / 4; i += Cfg::THREADS) {
+            for (int i = threadIdx.x; i < (Cfg::TROWS + 1) * KP / 4; i += blockDim.x) {
                 const int rr = (4 * i) / KP, cc = (4 * i) % KP;
-                *reinterpret_cast<float4*>(sA + rr * AP + cc) = (rr < rows_in) ? Wg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(sA + rr * AP + cc) = (rr < rows_here) ? Wg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         __syncthreads();
-        const int r = threadIdx.x;
-        const bool valid[2] = {f0 + r < F, f0 + r + HR < F};
-        float* ar[2] = {sA + r * AP, sA + (r + HR) * AP};
+        // threads 0..THREADS-1: rows r and r + ROWS/2; the extra warp: row ROWS + lane (second row unused)
+        const bool tailw = (int)threadIdx.x >= Cfg::THREADS;
+        const int r = tailw ? ROWS + ((int)threadIdx.x - Cfg::THREADS) : (int)threadIdx.x;
+        const int r1 = tailw ? Cfg::TROWS : r + HR;            // the extra warp's second row: the zero row, stays zero
+        const bool valid[2] = {r < rows_here, !tailw && r1 < rows_here};
+        float* ar[2] = {sA + r * AP, sA + r1 * AP};
         float fl[2] = {0.f, 0.f};
         if (tc_out.hbad) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
-                if (valid[rr]) fl[rr] = tc_out.fill[(long long)b * tc_out.fill_stride + f0 + r + rr * HR];
+            if (valid[0]) fl[0] = tc_out.fill[(long long)b * tc_out.fill_stride + f0 + r];
+            if (valid[1]) fl[1] = tc_out.fill[(long long)b * tc_out.fill_stride + f0 + r1];
         }
-        // F = 2^m + 1 leaves the last block of a clip with one row: warps without a valid row skip the sweep
+        // F = 2^m + 1: warps without a valid row skip the sweep
         if (__ballot_sync(0xffffffffu, valid[0]) != 0u) {
+        // -B (the X.Ht sums) of coordinate block c: split 0 is fetched one block ahead, raw, so that no warp waits for
+        // it (two warps per scheduler do not hide a global load); further splits (FFMA path only) are added in order
+        const float* pbase[2] = {partial + (((long long)b * S) * F + f0 + r) * KP, partial + (((long long)b * S) * F + f0 + r1) * KP};
+        float4 pn[2][2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            pn[rr][0] = pn[rr][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[rr]) { pn[rr][0] = *reinterpret_cast<const float4*>(pbase[rr]); pn[rr][1] = *reinterpret_cast<const float4*>(pbase[rr] + 4); }
+        }
 #pragma unroll 1
         for (int c = 0; c < KP; c += 8) {
-            float nb[2][8];
+            float4 pc[2][2];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) nb[rr][i] = 0.f;
-                if (valid[rr]) {
-                    for (int sp = 0; sp < S; ++sp) {           // fixed order -> deterministic
-                        const float* pr = partial + ((((long long)b * S + sp) * F) + f0 + r + rr * HR) * KP + c;
-                        const float4 v0 = *reinterpret_cast<const float4*>(pr), v1 = *reinterpret_cast<const float4*>(pr + 4);
-                        nb[rr][0] -= v0.x; nb[rr][1] -= v0.y; nb[rr][2] -= v0.z; nb[rr][3] -= v0.w;
-                        nb[rr][4] -= v1.x; nb[rr][5] -= v1.y; nb[rr][6] -= v1.z; nb[rr][7] -= v1.w;
-                    }
+                pc[rr][0] = pn[rr][0]; pc[rr][1] = pn[rr][1];
+                if (valid[rr] && c + 8 < KP) {
+                    pn[rr][0] = *reinterpret_cast<const float4*>(pbase[rr] + c + 8);
+                    pn[rr][1] = *reinterpret_cast<const float4*>(pbase[rr] + c + 12);
                 }
-            }
-            if (tc_out.hbad) {                                 // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
-                const float4 h0 = *reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP + c);
-                const float4 h1 = *reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP + c + 4);
-                const float hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) nb[rr][i] = fmaf(-fl[rr], hb[i], nb[rr][i]);
             }
             // gradient i of the block = row c+i of G . a: x accumulates the even, y the odd columns
             float2 acc[2][8];
@@ -134,6 +139,29 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                     acc[0][i] = fma2(make_float2(a0.z, a0.w), make_float2(u.z, u.w), acc[0][i]);
                     acc[1][i] = fma2(make_float2(a1.z, a1.w), make_float2(u.z, u.w), acc[1][i]);
                 }
+            }
+            float nb[2][8];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                nb[rr][0] = 0.f - pc[rr][0].x; nb[rr][1] = 0.f - pc[rr][0].y; nb[rr][2] = 0.f - pc[rr][0].z; nb[rr][3] = 0.f - pc[rr][0].w;
+                nb[rr][4] = 0.f - pc[rr][1].x; nb[rr][5] = 0.f - pc[rr][1].y; nb[rr][6] = 0.f - pc[rr][1].z; nb[rr][7] = 0.f - pc[rr][1].w;
+                if (valid[rr]) {
+                    for (int sp = 1; sp < S; ++sp) {           // fixed order -> deterministic
+                        const float* pr = pbase[rr] + (long long)sp * F * KP + c;
+                        const float4 v0 = *reinterpret_cast<const float4*>(pr), v1 = *reinterpret_cast<const float4*>(pr + 4);
+                        nb[rr][0] -= v0.x; nb[rr][1] -= v0.y; nb[rr][2] -= v0.z; nb[rr][3] -= v0.w;
+                        nb[rr][4] -= v1.x; nb[rr][5] -= v1.y; nb[rr][6] -= v1.z; nb[rr][7] -= v1.w;
+                    }
+                }
+            }
+            if (tc_out.hbad) {                                 // bad frames: X.Ht += fill[f] * (sum of their rows of Ht)
+                const float4 h0 = *reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP + c);
+                const float4 h1 = *reinterpret_cast<const float4*>(tc_out.hbad + (long long)b * KP + c + 4);
+                const float hb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nb[rr][i] = fmaf(-fl[rr], hb[i], nb[rr][i]);
             }
             float gr[2][8], aq[2][8];
 #pragma unroll
@@ -156,7 +184,7 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
                     const float a_ = aq[rr][i];
                     const float pg = (a_ == 0.f) ? fminf(0.f, grad) : grad;
                     vsum += fabsf(pg);                         // rows past the clip's last one: a = 0, B = 0 -> pg = 0
-                    if (pg_out && valid[rr]) pg_out[((long long)b * F + f0 + r + rr * HR) * KP + t] = fabsf(pg);
+                    if (pg_out && valid[rr]) pg_out[((long long)b * F + f0 + (rr ? r1 : r)) * KP + t] = fabsf(pg);
                     const float an = (inv != 0.f) ? fmaxf(fmaf(-grad, inv, a_), 0.f) : a_;
                     const float d = an - a_;
                     aq[rr][i] = an;
@@ -252,7 +280,6 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
     __syncthreads();
 
     // ---- the new rows: W ------------------------------------------------------------------------------------------
-    const int rows_here = min(ROWS, F - f0);
     float* Wb = W + (long long)b * w_stride + (long long)f0 * KP;
     for (int i = threadIdx.x; i < rows_here * KP / 4; i += blockDim.x)
         *reinterpret_cast<float4*>(Wb + 4 * i) = *reinterpret_cast<const float4*>(sA + ((4 * i) / KP) * AP + ((4 * i) % KP));
@@ -264,9 +291,9 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         float* WtX = tc_out.WtX + (long long)b * tc_out.wt_stride;
         // one item = (component k, group of 8 rows): consecutive lanes take consecutive k (conflict-free reads of the
         // tile's columns) and write 32 contiguous bytes of row k of each operand
-        for (int i = threadIdx.x; i < KP * (ROWS / 8); i += blockDim.x) {
+        for (int i = threadIdx.x; i < KP * (Cfg::TROWS / 8); i += blockDim.x) {
             const int k = i % KP, g8 = (i / KP) * 8, ff = f0 + g8;
-            if (ff >= tc_out.ldw) continue;
+            if (g8 >= rows_here || ff >= tc_out.ldw) continue;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = sA[(g8 + e) * AP + k];
@@ -294,7 +321,7 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
         }
     }
     // ---- this block's share of W^T W: thread (ty, tx) of a (THREADS/16) x 16 grid owns rows ty*TI.., columns pass*16*TJ + tx*TJ.. ----
-    {
+    if ((int)threadIdx.x < Cfg::THREADS) {
         constexpr int TY = Cfg::THREADS / 16, TI = KP / TY, TJ = (KP >= 64) ? 4 : 2, PASSES = KP / (16 * TJ);
         const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
         float* out = gram_partial + ((long long)b * P + blockIdx.x) * (KP * KP);
@@ -352,18 +379,20 @@ w_side_kernel(float* __restrict__ W, long long w_stride, int F, const float* __r
 
 }
 
-// W^T W = sum of the W-side kernel's partials in block order (deterministic), 8 rows per block, and (tensor-core path) the
-// H step's operands that derive from those 8 rows (g_prep_block); grid = (KP/8, B)
+// W^T W = sum of the W-side kernel's partials in block order (deterministic), 8 * gpb rows per block, and (tensor-core path)
+// the H step's operands that derive from those rows (g_prep_block per group of 8); grid = (KP / (8 * gpb), B).  gpb > 1 for
+// big batches: one block per clip instead of KP/8 (the kernel is a chain of dependent round trips; fewer, fatter blocks
+// finish in one wave).
 __global__ void __launch_bounds__(kThreads)
-w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P, int KP, float* __restrict__ WtW, WSideTc tc_out,
+w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P, int KP, int gpb, float* __restrict__ WtW, WSideTc tc_out,
                 const ClipState* __restrict__ st) {
-    const int b = blockIdx.y, blk = blockIdx.x;
+    const int b = blockIdx.y, blk0 = blockIdx.x * gpb, n_el = 8 * gpb * KP;
     if (st[b].done) return;
-    const float* pb = gram_partial + (long long)b * P * (KP * KP) + 8 * blk * KP;
+    const float* pb = gram_partial + (long long)b * P * (KP * KP) + 8 * blk0 * KP;
     float* Go = WtW + (long long)b * (KP * KP);
     // block-ordered sums (deterministic); the loads of a group of partials are issued together -- with one long signal
     // this kernel is KP/8 blocks and its duration is the latency of P dependent round trips otherwise
-    for (int e0 = 0; e0 < 8 * KP; e0 += 4 * blockDim.x) {
+    for (int e0 = 0; e0 < n_el; e0 += 4 * blockDim.x) {
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         for (int q0 = 0; q0 < P; q0 += 8) {
             float v[8][4];
@@ -372,7 +401,7 @@ w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P,
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     const int e = e0 + m * blockDim.x + threadIdx.x;
-                    v[q][m] = (q0 + q < P && e < 8 * KP) ? pb[(long long)(q0 + q) * (KP * KP) + e] : 0.f;
+                    v[q][m] = (q0 + q < P && e < n_el) ? pb[(long long)(q0 + q) * (KP * KP) + e] : 0.f;
                 }
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -382,19 +411,22 @@ w_finish_kernel(const float* __restrict__ gram_partial /*[B][P][KP*KP]*/, int P,
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int e = e0 + m * blockDim.x + threadIdx.x;
-            if (e < 8 * KP) Go[8 * blk * KP + e] = sum[m];
+            if (e < n_el) Go[8 * blk0 * KP + e] = sum[m];
         }
     }
 #ifndef AINMF_EMU
     if (tc_out.blobs) {
         __syncthreads();                                 // the rows just written are read back by other threads of the block
-        g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
-                     tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
-        if (threadIdx.x < 8) {                           // v[8blk + j] = fill^T.W: the X^T.W row of every bad frame
-            if (tc_out.vpartial) {
+        for (int sub = 0; sub < gpb; ++sub) {
+            const int blk = blk0 + sub;
+            g_prep_block(Go, tc_out.GX + (long long)b * KP * KP, tc_out.blobs + ((long long)b * (KP / 8) + blk) * (16 * KP),
+                         tc_out.scal + ((long long)b * (KP / 8) + blk) * TS_SC, KP, blk, threadIdx.x, blockDim.x);
+        }
+        if (tc_out.vpartial) {                           // v[k] = fill^T.W: the X^T.W row of every bad frame
+            for (int k = threadIdx.x; k < 8 * gpb; k += blockDim.x) {
                 float v = 0.f;
-                for (int q = 0; q < P; ++q) v += tc_out.vpartial[((long long)b * P + q) * KP + 8 * blk + threadIdx.x];
-                tc_out.vfill[(long long)b * KP + 8 * blk + threadIdx.x] = v;
+                for (int q = 0; q < P; ++q) v += tc_out.vpartial[((long long)b * P + q) * KP + 8 * blk0 + k];
+                tc_out.vfill[(long long)b * KP + 8 * blk0 + k] = v;
             }
         }
     }
@@ -414,7 +446,7 @@ static cudaError_t launch_w_side_impl(const NmfProblem& p, const NmfWork& wk, in
         auto kern = w_side_kernel<KP, WC::L, WC::ROWS>;
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC::smem_bytes);
         if (e2 != cudaSuccess) return e2;
-        AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
+        AINMF_LAUNCH(kern, dim3(wk.nW, p.B), dim3(WC::LAUNCH_THREADS), WC::smem_bytes, s, p.W, p.w_stride, p.F, wk.HHt,
                      wk.xht_reduced ? wk.xht_reduced : wk.xht_partial, wk.xht_reduced ? 1 : S, wk.violW, wk.gram_partial,
                      tco, p.state, wk.exact_viol ? wk.pgW : nullptr);
         return cudaGetLastError();
@@ -427,7 +459,8 @@ static cudaError_t launch_w_side_impl(const NmfProblem& p, const NmfWork& wk, in
     else if (lanes >= 2) e = launch(WSideCfg<KP, 2, 128>{});
     else { if constexpr (LMIN <= 1) e = launch(WSideCfg<KP, 1, 256>{}); }
     if (e != cudaSuccess) return e;
-    AINMF_LAUNCH(w_finish_kernel, dim3(KP / 8, p.B), dim3(kThreads), 0, s, wk.gram_partial, wk.nW, KP, wk.WtW, tco, p.state);
+    const int gpb = (wk.finish_gpb >= 1 && (KP / 8) % wk.finish_gpb == 0) ? wk.finish_gpb : 1;
+    AINMF_LAUNCH(w_finish_kernel, dim3(KP / 8 / gpb, p.B), dim3(kThreads), 0, s, wk.gram_partial, wk.nW, KP, gpb, wk.WtW, tco, p.state);
     return cudaGetLastError();
 }
 

@@ -60,11 +60,12 @@ def test_emu_nmf_fit(F, T, K, iters):
     assert rel_l2(W[0], Wo) < 1e-4 and rel_l2(H[0], Ho) < 1e-4
 
 
-@pytest.mark.parametrize("F,T,K,B,iters", [(129, 50, 40, 4, 3), (140, 36, 20, 8, 3)])
+@pytest.mark.parametrize("F,T,K,B,iters", [(129, 50, 40, 4, 3), (140, 36, 20, 8, 3), (258, 24, 40, 4, 2), (261, 20, 24, 4, 2)])
 def test_emu_nmf_fit_batch_one_thread_per_row_w_side(F, T, K, B, iters):
     """A batch large enough (for the emulator's 4 SMs) that the W side takes its one-thread-per-row shape: the blocked
     sweep (blocks of 8 coordinates, in-block corrections) must reproduce sklearn's sequential sweep; F = 129 leaves the
-    last block of every clip with a single row (as F = 513 does at the real sizes)."""
+    last block of every clip with a single row (as F = 513 does at the real sizes); F = 258 / 261 are 256 rows plus a
+    remainder that rides with the last block on its extra warp (nmf_wside.cu: TAIL)."""
     rng = np.random.default_rng(F + B)
     X = np.abs(rng.standard_normal((B, F, T))).astype(np.float32)
     X[1, :, 5:9] = 0.0                                     # a clip with zero columns: some coordinates hit the bound
