@@ -5,7 +5,7 @@ import ctypes as C
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WORKSPACE, ERR_ALL_BAD, ERR_COMM = -1, -2, -3, -4, -5, -6
-SOLVER_CD, SOLVER_MU = 0, 1
+SOLVER_CD, SOLVER_MU, SOLVER_MU_KL = 0, 1, 2
 
 EXPORTS = [
     "ainmf_create", "ainmf_destroy", "ainmf_last_error", "ainmf_version", "ainmf_params_default",

@@ -276,7 +276,7 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     if (p->rank < 1 || p->rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", p->rank);
     if (p->max_iter < 1) return fail(h, AINMF_ERR_INVALID, "max_iter must be >= 1");
     if (!(p->tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "tol must be >= 0");
-    if (p->solver != AINMF_SOLVER_CD && p->solver != AINMF_SOLVER_MU) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu)", p->solver);
+    if (p->solver != AINMF_SOLVER_CD && p->solver != AINMF_SOLVER_MU && p->solver != AINMF_SOLVER_MU_KL) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu, 2 = mu with the Kullback-Leibler divergence)", p->solver);
     if (p->n_outer < 1) return fail(h, AINMF_ERR_INVALID, "n_outer must be >= 1");
     if (geometry(p->n_samples, p->n_fft, p->hop, &pl->g)) return fail(h, AINMF_ERR_INVALID, "signal too long");
     if (p->col_start >= 0) {
@@ -291,7 +291,7 @@ int make_plan(ainmf_handle h, const ainmf_params* p, Plan* pl) {
     const int KP = pl->KP;
     impute_plan(T, &pl->iw);
     nmf_plan(B, T, F, KP, h->n_sm, &pl->nw);
-    if (p->solver == AINMF_SOLVER_MU) { pl->nw.want_mu = 1; pl->nw.use_tc = 0; pl->nw.exact_viol = 0; }
+    if (p->solver != AINMF_SOLVER_CD) { pl->nw.want_mu = (p->solver == AINMF_SOLVER_MU_KL) ? 2 : 1; pl->nw.use_tc = 0; pl->nw.exact_viol = 0; }
     pl->vz_stride = (long long)T * ldf;
     pl->bad_stride = round_up(T, 16);
     pl->w_stride = (long long)F * KP;
@@ -372,14 +372,16 @@ __global__ void copy_indices_kernel(const int* __restrict__ idx, const ClipState
 // extra iterations queued after the last clip converged do nothing and every clip's n_iter is exact.
 int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, int max_iter, float tol, int* d_flag,
                    cudaStream_t s) {
-    const bool mu = prob.solver == AINMF_SOLVER_MU;
+    const bool kl = prob.solver == AINMF_SOLVER_MU_KL;
+    const bool mu = prob.solver == AINMF_SOLVER_MU || kl;
     const int poll = mu ? 10 : 8;          // MU tests convergence every 10th iteration only
-    if (mu && tol > 0.f) CU(h, nmf_mu_begin(prob, nw, s));
+    if (mu && tol > 0.f) CU(h, kl ? nmf_mukl_begin(prob, nw, s) : nmf_mu_begin(prob, nw, s));
     if (tol > 0.f && !h->ev_poll[0])
         for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
     int pending = -1;
     for (int it = 1; it <= max_iter; ++it) {
-        if (mu) CU(h, nmf_mu_iterate(prob, nw, it, s));
+        if (kl) CU(h, nmf_mukl_iterate(prob, nw, it, s));
+        else if (mu) CU(h, nmf_mu_iterate(prob, nw, it, s));
         else CU(h, nmf_cd_iterate(prob, nw, it, s));
         if (tol > 0.f && (it % poll == 0) && it < max_iter) {
             const int g = (it / poll) & 1;
@@ -567,7 +569,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     if (!X_ft || batch <= 0 || F < 1 || T < 1) return fail(h, AINMF_ERR_INVALID, "bad argument to ainmf_nmf_fit");
     if (rank < 1 || rank > 128) return fail(h, AINMF_ERR_INVALID, "rank must be in [1,128], got %d", rank);
     if (max_iter < 1 || !(tol >= 0.f)) return fail(h, AINMF_ERR_INVALID, "need max_iter >= 1 and tol >= 0");
-    if (solver != AINMF_SOLVER_CD && solver != AINMF_SOLVER_MU) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu)", solver);
+    if (solver != AINMF_SOLVER_CD && solver != AINMF_SOLVER_MU && solver != AINMF_SOLVER_MU_KL) return fail(h, AINMF_ERR_INVALID, "unknown solver %d (0 = cd, 1 = mu, 2 = mu with the Kullback-Leibler divergence)", solver);
     if ((W0 == nullptr) != (H0 == nullptr)) return fail(h, AINMF_ERR_INVALID, "W0 and H0 must be given together");
     cudaStream_t s = (cudaStream_t)stream;
     CU(h, cudaSetDevice(h->device));
@@ -576,7 +578,7 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
     NmfWork nw;
     impute_plan(T, &iw);
     nmf_plan(B, T, F, KP, h->n_sm, &nw);
-    if (solver == AINMF_SOLVER_MU) { nw.want_mu = 1; nw.use_tc = 0; nw.exact_viol = 0; }
+    if (solver != AINMF_SOLVER_CD) { nw.want_mu = (solver == AINMF_SOLVER_MU_KL) ? 2 : 1; nw.use_tc = 0; nw.exact_viol = 0; }
     const long long xs = (long long)T * ldf, ws = (long long)F * KP, hs = (long long)T * KP;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
@@ -614,7 +616,9 @@ int ainmf_nmf_fit(ainmf_handle h, const float* X_ft, int32_t batch, int32_t F, i
         CU(h, launch_init_factors(Wn, Hn, T, 0, B, F, T, rank, KP, pr.state, pr.W, ws, pr.Ht, hs, s));
     }
     if ((rc = run_iterations(h, pr, nw, max_iter, tol, (int*)(base + oF), s))) return rc;
+    if (solver == AINMF_SOLVER_MU_KL) CU(h, nmf_mukl_error(pr, nw, true, s));      // reconstruction_err_ = sqrt(2 D_KL)
     CU(h, nmf_finalize(pr, nw, nobad, round_up(T, 16), s));
+    if (solver == AINMF_SOLVER_MU_KL) CU(h, nmf_mukl_set_err(pr, nw, s));
     CU(h, launch_unpack_factors(pr.W, ws, pr.Ht, hs, B, F, T, rank, KP, W, H, s));
     CU(h, launch_export_state(pr.state, B, nullptr, n_iter, err, nullptr, s));
     return AINMF_OK;
@@ -769,7 +773,9 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
             if ((rc = run_iterations(h, prf, pl.nw, p->max_iter, p->tol, d_flag, s))) return rc;
             if (pl.compact) CU(h, launch_scatter_rows(prf.Ht, pr.h_stride, pr.Ht, pr.h_stride, KP, perm, B, T, s));
             // a8 + a9: objective, then bad frames <- (W H) frames
+            if (p->solver == AINMF_SOLVER_MU_KL) CU(h, nmf_mukl_error(pr, pl.nw, true, s));
             CU(h, nmf_finalize(pr, pl.nw, bad, pl.bad_stride, s));
+            if (p->solver == AINMF_SOLVER_MU_KL) CU(h, nmf_mukl_set_err(pr, pl.nw, s));
         }
     }
     // a10 + a11: recombine with the corrupted phase, inverse STFT, trim

@@ -152,7 +152,7 @@ void prof_collect(double* ms /*[PROF_KINDS]*/, long long* counts /*[PROF_KINDS]*
 // ---- nmf_cd.cu ----------------------------------------------------------------------------------
 struct NmfProblem {
     int B, T, F, ldf, KP;
-    int solver = 0;                     // 0 = coordinate descent (the reference's), 1 = multiplicative update (Frobenius)
+    int solver = 0;                     // 0 = coordinate descent (the reference's), 1 = multiplicative update (Frobenius), 2 = MU (Kullback-Leibler)
     float tol;
     float* Xt; long long x_stride;      // [B][T][ldf]
     float* W; long long w_stride;       // [B][F][KP]
@@ -193,11 +193,14 @@ struct NmfWork {
     // time-frame-sharded mode only (B == 1); null otherwise
     float* xht_reduced = nullptr;       // [F][KP]: local X.Ht summed over the splits = first part of the all-reduce buffer
     double* h_viol_sum = nullptr;       // [B]: local H-side violation, all-reduced by the caller before the stop rule
+    float* h_viol_pack = nullptr;       // [B][4]: the same as hi/lo floats, for a caller that sends it with the next float all-reduce
     // multiplicative-update solver
     float* xtw = nullptr;               // [B][T][KP]: X^T.W (the MU numerator of the H update)
     unsigned char* zero_flags = nullptr;  // [B][zero_stride] zeros: error evaluation that must not overwrite frames
     long long zero_stride = 0;
-    int want_mu = 0;                    // set before nmf_work_bytes / nmf_carve when solver == MU
+    int want_mu = 0;                    // set before nmf_work_bytes / nmf_carve: 1 = MU (Frobenius), 2 = MU (Kullback-Leibler)
+    float* kl_sums = nullptr;           // MU-KL: [2][B][KP] row sums of H, column sums of W (the denominators)
+    double* kl_err = nullptr;           // MU-KL: [B] final divergence (kept across nmf_finalize, which reports the Frobenius error)
 };
 enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4 };
 void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
@@ -215,6 +218,16 @@ cudaError_t nmf_cd_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaS
 // W and H update and, every 10th iteration when tol > 0, the convergence test.
 cudaError_t nmf_mu_begin(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);
 cudaError_t nmf_mu_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
+cudaError_t nmf_mu_tick(const NmfProblem& p, int it, cudaStream_t s);     // n_iter = it for the clips still iterating
+cudaError_t nmf_mu_stop(const NmfProblem& p, int it, cudaStream_t s);     // the every-10th-iteration test on state.err
+// nmf_mukl.cu: multiplicative update, generalised Kullback-Leibler divergence (sklearn solver='mu',
+// beta_loss='kullback-leibler': _nmf.py:551-626, 636-721, 129-154, 862-879), one fused kernel per half-step.
+// nmf_mukl_error writes sqrt(2 D_KL) to state.err (keep = false) or to wk.kl_err (keep = true: the final value, computed
+// before nmf_finalize replaces frames; nmf_mukl_set_err puts it back into state.err afterwards).
+cudaError_t nmf_mukl_begin(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);
+cudaError_t nmf_mukl_iterate(const NmfProblem& p, const NmfWork& wk, int it, cudaStream_t s);
+cudaError_t nmf_mukl_error(const NmfProblem& p, const NmfWork& wk, bool keep, cudaStream_t s);
+cudaError_t nmf_mukl_set_err(const NmfProblem& p, const NmfWork& wk, cudaStream_t s);
 // the same iteration in pieces, so that a collective can be placed between them (time-sharded mode):
 // PARTIALS: HHt and X.Ht of the local frames; UPDATE: W sweep, WtW, fused X^T.W + H sweep; STOP: the stop rule
 cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int phases, cudaStream_t s);

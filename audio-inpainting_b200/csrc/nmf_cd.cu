@@ -659,14 +659,20 @@ reduce_partials_kernel(const float* __restrict__ partial, int S, long long n4, f
 }
 // out[b] = sum_i v[b][i] in double (one warp per clip)
 __global__ void __launch_bounds__(kThreads)
-viol_sum_kernel(const float* __restrict__ v, int n, int B, double* __restrict__ out) {
+viol_sum_kernel(const float* __restrict__ v, int n, int B, double* __restrict__ out, float* __restrict__ pack) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
     double s = 0.0;
     for (int i = lane; i < n; i += 32) s += (double)v[(long long)b * n + i];
     s = warp_sum_d(s);
-    if (lane == 0) out[b] = s;
+    if (lane == 0) {
+        out[b] = s;
+        if (pack) {              // the same sum as two floats (hi + lo) riding at the end of the next float all-reduce
+            const float hi = (float)s;
+            pack[4 * b] = hi; pack[4 * b + 1] = (float)(s - (double)hi); pack[4 * b + 2] = 0.f; pack[4 * b + 3] = 0.f;
+        }
+    }
 }
 
 template <int KP>
@@ -722,7 +728,7 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
         prof_end(PROF_H_STEP, s);
         if (wk.h_viol_sum) {      // time-sharded mode: local H-side violation as one double for the all-reduce
             AINMF_LAUNCH(viol_sum_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, wk.violH, wk.nH,
-                         p.B, wk.h_viol_sum);
+                         p.B, wk.h_viol_sum, wk.h_viol_pack);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         }
     }
@@ -898,6 +904,14 @@ static cudaError_t mu_iterate_impl(const NmfProblem& p, const NmfWork& wk, int i
     return cudaSuccess;
 }
 
+cudaError_t nmf_mu_tick(const NmfProblem& p, int it, cudaStream_t s) {
+    AINMF_LAUNCH(mu_tick_kernel, dim3(ceil_div(p.B, kThreads)), dim3(kThreads), 0, s, p.state, p.B, it);
+    return cudaGetLastError();
+}
+cudaError_t nmf_mu_stop(const NmfProblem& p, int it, cudaStream_t s) {
+    AINMF_LAUNCH(mu_stop_kernel, dim3(ceil_div(p.B, kThreads)), dim3(kThreads), 0, s, p.state, p.B, it, p.tol);
+    return cudaGetLastError();
+}
 cudaError_t nmf_mu_begin(const NmfProblem& p, const NmfWork& wk, cudaStream_t s) {
     switch (p.KP) {
         case 32: return mu_error<32>(p, wk, 0, s);
@@ -1001,7 +1015,8 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
                        + al256(sizeof(float) * (size_t)B * wk.nW * KP) + 2 * al256(sizeof(float) * (size_t)B * KP) + al256(sizeof(float) * (size_t)B * wk.hbad_blocks * KP); // fill^T.W partials, bad-frame sums of Ht, fill^T.W, hbad shares
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
-    if (wk.want_mu) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
+    if (wk.want_mu == 1) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
+    if (wk.want_mu == 2) n += al256(sizeof(float) * (size_t)B * 2 * KP) + al256(sizeof(double) * (size_t)B);
     if (wk.exact_viol) n += al256(sizeof(float) * (size_t)B * F * KP) + al256(sizeof(float) * (size_t)B * T * KP);
     return n;
 }
@@ -1031,7 +1046,11 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);
     wk->err_partial = (double*)take(sizeof(double) * (size_t)B * ceil_div(T, 16));
-    if (wk->want_mu) {
+    if (wk->want_mu == 2) {
+        wk->kl_sums = (float*)take(sizeof(float) * (size_t)B * 2 * KP);
+        wk->kl_err = (double*)take(sizeof(double) * (size_t)B);
+    }
+    if (wk->want_mu == 1) {
         wk->xtw = (float*)take(sizeof(float) * (size_t)B * T * KP);
         wk->zero_stride = round_up(T, 16);
         wk->zero_flags = (unsigned char*)take((size_t)B * wk->zero_stride);      // the caller zeroes it once

@@ -116,10 +116,10 @@ def _gap_mask(x, hop, n_frames, threshold, frac_num, frac_den):
 
 def _solver_id(solver: str) -> int:
     try:
-        return {"cd": _capi.SOLVER_CD, "mu": _capi.SOLVER_MU}[solver]
+        return {"cd": _capi.SOLVER_CD, "mu": _capi.SOLVER_MU, "mu-kl": _capi.SOLVER_MU_KL}[solver]
     except KeyError:
         raise RuntimeError(f"unknown solver {solver!r}: 'cd' (sklearn coordinate descent, what the reference runs) or "
-                           "'mu' (multiplicative update, Frobenius)") from None
+                           "'mu' (multiplicative update, Frobenius), 'mu-kl' (multiplicative update, Kullback-Leibler)") from None
 
 
 def _nmf_fit(X, rank, max_iter, tol, seed, W0, H0, solver="cd"):

@@ -15,6 +15,7 @@ The same JSON line carries, as objects next to the headline keys (--legs, defaul
                   sharded H + all-reduce of the W partial sums at N > 1 (strong scaling); with its own e2e, roofline, parity
                   against the oracle on a prefix and (N = 1) a same-box CPU figure;
   "c4_full_4096"  (N = 1) all 4096 clips of configs[3] on one GPU through ainmf_inpaint_host (chunked by free memory);
+  "mu_kl"         (N = 1) the multiplicative-update / Kullback-Leibler solver (north_star (3)'s ratio form) on the c4 shape;
   "latency_cases" (N = 1) configs[0], [1], [2]: main4_NMF.py's 50 chained refits on the real segment, one 10 s clip with a
                   2 s gap at 2048/512, one clip with the random-fragment mask; each with the CPU path beside it.
 `--impl reference` times the reference's own CPU path (scipy + sklearn through oracle/libcalls.py) for the same workloads.
@@ -767,6 +768,44 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def leg_mu_kl(ctx, cpu):
+    """north_star (3)'s multiplicative-update form (solver 'mu-kl': W.H, X / (W.H) and both contractions fused per half-step,
+    nmf_mukl.cu) on spectrograms of the c4 shape: ms per iteration over a batch, as a fraction of the HBM roofline (an
+    iteration reads X twice: 8 F T bytes + factors) and of the FP32 rate it is actually bound by (8 F T K flops);
+    sklearn's solver='mu', beta_loss='kullback-leibler' on one spectrogram beside it, with the parity of that one."""
+    torch = ctx.torch
+    F, T, K, B, iters = 513, 1724, 64, 256, 10
+    g = torch.Generator(device=ctx.device).manual_seed(1)
+    X = torch.rand((B, F, T), device=ctx.device, generator=g) ** 2
+    ctx.ops.nmf_fit(X, K, 2, 0.0, 42, None, None, "mu-kl")
+    ctx.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(); ctx.ops.nmf_fit(X, K, 2, 0.0, 42, None, None, "mu-kl")
+    e1.record(); W, H, err, nit = ctx.ops.nmf_fit(X, K, 2 + iters, 0.0, 42, None, None, "mu-kl")
+    e2.record(); torch.cuda.synchronize()
+    ms_it = (e1.elapsed_time(e2) - e0.elapsed_time(e1)) / iters          # the fixed costs (transpose, init, error) cancel
+    bytes_it = (8.0 * F * T + 12.0 * K * (F + T)) * B
+    flops_it = 8.0 * F * T * K * B
+    peak, src = peaks()
+    out = {"workload": f"{B} spectrograms {F} x {T}, K = {K}: multiplicative update, Kullback-Leibler divergence (ratio form), fused FFMA kernels",
+           "ms_per_iteration": ms_it, "nmf_iters_per_s": 1e3 * B / ms_it, "hbm_frac": bytes_it / (ms_it * 1e-3) / 1e9 / peak,
+           "fp32_tflops": flops_it / (ms_it * 1e-3) / 1e12, "bound": "fp32 FMA pipe (8 F T K flops against 8 F T bytes: 64 flop/B at K = 64)"}
+    if cpu:
+        from oracle import libcalls
+        cores = use_all_host_threads()
+        x1 = X[0].cpu().numpy()
+        t0 = time.perf_counter()
+        Wo, Ho, no, eo = libcalls.nmf_fit(x1, K, seed=42, max_iter=12, tol=0.0, solver="mu", beta_loss="kullback-leibler")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"nmf_iters_per_s": 12 / dt, "cores": cores, "kind": "port",
+                               "sample": "12 iterations of sklearn NMF(solver='mu', beta_loss='kullback-leibler') on one spectrogram"}
+        out["parity"] = {"objective_rel_diff": abs(float(err[0]) - eo) / eo, "n_iter": [int(nit[0]), no]}
+        out["speedup_vs_cpu"] = out["nmf_iters_per_s"] / out["cpu_baseline"]["nmf_iters_per_s"]
+    del X
+    ctx.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=0.0, help="c5 only: signal length override")
@@ -776,8 +815,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the workload's)")
-    ap.add_argument("--legs", default="c5,c4_full,latency", help="extra objects of the default (c4) line: comma list of c5, c4_full, "
-                                                                 "latency; 'none' for the headline only")
+    ap.add_argument("--legs", default="c5,c4_full,latency,mu_kl", help="extra objects of the default (c4) line: comma list of c5, c4_full, "
+                                                                 "latency, mu_kl; 'none' for the headline only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.legs = [] if args.legs == "none" else [s for s in args.legs.split(",") if s]
@@ -815,6 +854,8 @@ def main():
                     lat[nm] = {k: r[k] for k in ("value", "unit", "ms_per_step", "config", "cold_first_call_ms", "e2e", "cpu_baseline", "parity", "nmf_iters_per_s")}
                     lat[nm]["ms_per_iteration"] = r["roofline"]["iteration"]["ms_per_iteration"]
                 line["latency_cases"] = lat
+            if ctx.world == 1 and "mu_kl" in args.legs:
+                line["mu_kl"] = leg_mu_kl(ctx, cpu)
     if ctx.rank == 0:
         print(json.dumps(line), flush=True)
     if ctx.world > 1:

@@ -46,7 +46,9 @@ enum ainmf_status {
 
 enum ainmf_solver {
     AINMF_SOLVER_CD = 0,        /* sklearn solver='cd', beta_loss='frobenius' -- what the reference runs */
-    AINMF_SOLVER_MU = 1         /* multiplicative update, Frobenius (sklearn solver='mu') */
+    AINMF_SOLVER_MU = 1,        /* multiplicative update, Frobenius (sklearn solver='mu') */
+    AINMF_SOLVER_MU_KL = 2      /* multiplicative update, generalised Kullback-Leibler divergence (sklearn solver='mu',
+                                   beta_loss='kullback-leibler'): the masked-ratio form X / (W H); err = sqrt(2 D_KL) */
 };
 
 /* Parameters of one inpainting problem.  Defaults of the reference in brackets. */

@@ -164,6 +164,23 @@ def test_emu_mu_solver_matches_sklearn_mu(F, T, K, iters, tol):
     assert rel_l2(W[0], Wo) < 1e-3 and rel_l2(H[0], Ho) < 1e-3
 
 
+@pytest.mark.parametrize("F,T,K,iters,tol", [(65, 95, 8, 12, 0.0), (70, 130, 40, 6, 0.0), (40, 60, 6, 40, 1e-3)])
+def test_emu_mu_kl_solver_matches_sklearn(F, T, K, iters, tol):
+    """solver='mu-kl' (fused ratio kernels, nmf_mukl.cu) against sklearn solver='mu', beta_loss='kullback-leibler' from
+    the same initial factors: factors, n_iter_ (every-10th-iteration test) and reconstruction_err_ = sqrt(2 D_KL).
+    Zero columns exercise the x <= eps and W.H < eps branches."""
+    rng = np.random.default_rng(F + K)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    X[:, 7:11] = 0.0
+    X[3, :] = 0.0
+    W0, Ht0 = restate.init_factors(X.mean(), F, T, K, 3)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, W0=W0, H0=Ht0.T, max_iter=iters, tol=tol, solver="mu", beta_loss="kullback-leibler")
+    W, H, err, nit = E.nmf_fit(X, K, max_iter=iters, tol=tol, W0=W0, H0=np.ascontiguousarray(Ht0.T), solver=E.capi.SOLVER_MU_KL)
+    assert nit[0] == no
+    assert abs(err[0] - eo) < 1e-4 * eo
+    assert rel_l2(W[0], Wo) < 1e-3 and rel_l2(H[0], Ho) < 1e-3
+
+
 # ---- callers / baselines either side of the NMF path (SURVEY 8f-3, 8f-4) ---------------------------------------
 def _gap_signals():
     rng = np.random.default_rng(7)

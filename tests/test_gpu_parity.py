@@ -535,6 +535,35 @@ def test_mu_solver_matches_sklearn_mu(ops, F, T, K, iters, tol):
     assert rel_l2(W[0].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 1e-3
 
 
+@pytest.mark.parametrize("F,T,K,iters,tol", [(129, 200, 16, 25, 0.0), (513, 431, 40, 12, 0.0), (1025, 300, 128, 6, 0.0),
+                                              (100, 257, 24, 200, 1e-3)])
+def test_mu_kl_solver_matches_sklearn(ops, F, T, K, iters, tol):
+    """solver='mu-kl' -- north_star (3)'s form: W.H, the ratio X / (W.H) and both contractions in one fused kernel per
+    half-step (nmf_mukl.cu) -- against sklearn solver='mu', beta_loss='kullback-leibler' from the same initial factors:
+    n_iter_ (every-10th-iteration test), reconstruction_err_ = sqrt(2 D_KL) within 1e-4, factors within 1e-3.  Zero rows
+    and columns exercise the x <= eps and W.H < eps branches."""
+    rng = np.random.default_rng(F + K)
+    X = np.abs(rng.standard_normal((F, T))).astype(np.float32)
+    X[:, 7:11] = 0.0
+    X[3, :] = 0.0
+    W0, Ht0 = restate.init_factors(X.mean(), F, T, K, 3)
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, W0=W0, H0=Ht0.T, max_iter=iters, tol=tol, solver="mu", beta_loss="kullback-leibler")
+    W, H, err, nit = ops.nmf_fit(dev(X[None]), K, iters, tol, 0, dev(W0[None]), dev(np.ascontiguousarray(Ht0.T)[None]), "mu-kl")
+    assert int(nit[0]) == no
+    assert abs(float(err[0]) - eo) <= 1e-4 * eo
+    assert rel_l2(W[0].cpu().numpy(), Wo) < 1e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 1e-3
+
+
+def test_mu_kl_batch_is_independent(ops):
+    """A batch of clips through the fused KL kernels equals the clips fitted one by one, bit for bit."""
+    rng = np.random.default_rng(5)
+    X = np.abs(rng.standard_normal((3, 257, 150))).astype(np.float32)
+    Wb, Hb, eb, nb = ops.nmf_fit(dev(X), 20, 15, 0.0, 7, None, None, "mu-kl")
+    for b in range(3):
+        W1, H1, e1, n1 = ops.nmf_fit(dev(X[b:b + 1]), 20, 15, 0.0, 7, None, None, "mu-kl")
+        assert torch.equal(W1[0], Wb[b]) and torch.equal(H1[0], Hb[b]) and float(e1[0]) == float(eb[b])
+
+
 def test_ffma_path_still_matches_when_tensor_cores_disabled(ops, golden):
     """AINMF_DISABLE_TC=1 routes K >= 64 problems through the FFMA kernels; both paths must satisfy the same gates."""
     import os

@@ -73,18 +73,23 @@ def _worker(rank, world, port, N, kw, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_time_sharded_equals_single_rank(world, tmp_path):
+@pytest.mark.parametrize("world,max_iter,tol", [(2, 6, 1e-4), (3, 6, 1e-4), (2, 40, 5e-2)])
+def test_time_sharded_equals_single_rank(world, max_iter, tol, tmp_path):
+    """The third case stops early (tol = 5e-2): the H-side violation of an iteration travels with the next iteration's
+    exchange and the rule is evaluated one exchange late, before anything is updated -- n_iter and the factors must
+    still be those of the iteration at which sklearn stops."""
     import torch.multiprocessing as mp
     import emu_harness as E
     from oracle import libcalls
     N = 10000
-    kw = dict(n_fft=128, hop=32, rank=8, max_iter=6, tol=1e-4, seed=42)
+    kw = dict(n_fft=128, hop=32, rank=8, max_iter=max_iter, tol=tol, seed=42)
     port = 29500 + (os.getpid() % 1000) + world
     mp.spawn(_worker, args=(world, port, N, kw, str(tmp_path)), nprocs=world, join=True)
     x = _signal(N)
     single = E.inpaint(x, **kw)
-    yo, st = libcalls.restore_columns(x, 8000, n_fft=128, hop=32, K=8, seed=42, max_iter=6, return_all=True)
+    yo, st = libcalls.restore_columns(x, 8000, n_fft=128, hop=32, K=8, seed=42, max_iter=max_iter, tol=tol, return_all=True)
+    if max_iter > 6:
+        assert 1 < st["n_iter"] < max_iter                               # the case is an early stop
     y = np.zeros(N, np.float32)
     cover = np.zeros(N, np.int32)
     H = np.zeros((8, single["H"].shape[2]), np.float32)
