@@ -8,6 +8,7 @@
 
 #include <new>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/ainmf.h"
@@ -829,6 +830,10 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         if (m * h->n_sm < chunk) chunk = m * h->n_sm;
         else if (chunk >= h->n_sm) chunk = chunk / h->n_sm * h->n_sm;
     }
+    if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk
+        const long long v = atoll(ev);
+        if (v >= 1 && v < chunk) chunk = v;
+    }
     ainmf_params cp = *p;
     cp.batch = (int32_t)chunk;
     const size_t ws = ainmf_workspace_bytes(h, &cp);
@@ -854,40 +859,76 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
             CU(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
         }
     }
+    void* pin;
+    if ((rc = get_pinned(h, 3 * sizeof(int) * (size_t)p->batch, &pin))) return rc;
+    int* stage_nb = (int*)pin;
+    float* stage_er = (float*)(stage_nb + p->batch);
+    int* stage_ni = (int*)(stage_er + p->batch);
     const long long n_chunks = (p->batch + chunk - 1) / chunk;
     auto chunk_size = [&](long long c) { const long long b0 = c * chunk; return (int)((p->batch - b0 < chunk) ? p->batch - b0 : chunk); };
+    const bool trace = getenv("AINMF_HOST_TRACE") != nullptr;   // host wall-clock of the phases, device time of every chunk's copies and fit
+    std::vector<cudaEvent_t> tev, cev;
+    auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); } };
     auto copy_in = [&](long long c) -> int {
         const int j = (int)(c & 1);
         if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_in, h->ev_done[j], 0));       // the fit of chunk c-2 has read this x buffer
+        mark(cev, h->st_in);
         CU(h, cudaMemcpyAsync(base + oX[j], x_host + c * chunk * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
+        mark(cev, h->st_in);
         CU(h, cudaEventRecord(h->ev_in[j], h->st_in));
         return 0;
     };
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    std::vector<cudaEvent_t> oev;
     rc = AINMF_OK;
     if ((rc = copy_in(0))) return rc;
     for (long long c = 0; c < n_chunks && rc == AINMF_OK; ++c) {
+        if (trace) fprintf(stderr, "[ainmf host] chunk %lld: enqueue starts at %.2f ms\n", c, since());
         const int j = (int)(c & 1), nb = chunk_size(c);
         const long long b0 = c * chunk;
         if (c + 1 < n_chunks && (rc = copy_in(c + 1))) break;                      // enqueued before the fit blocks this thread at its polls
         cp.batch = nb;
         CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_in[j], 0));
         if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_out[j], 0));        // the result of chunk c-2 has left this y buffer
+        mark(tev, h->st_cmp);
         rc = ainmf_inpaint(h, &cp, (const float*)(base + oX[j]), nullptr, nullptr, (float*)(base + oY[j]), nullptr,
                            (int*)(base + oNb[j]), nullptr, nullptr, (float*)(base + oEr[j]), (int*)(base + oNi[j]), base + oWs, ws, h->st_cmp);
         if (rc) break;
+        mark(tev, h->st_cmp);
         CU(h, cudaEventRecord(h->ev_done[j], h->st_cmp));
         CU(h, cudaStreamWaitEvent(h->st_out, h->ev_done[j], 0));
+        mark(oev, h->st_out);
         CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY[j], sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
-        if (n_bad_host) CU(h, cudaMemcpyAsync(n_bad_host + b0, base + oNb[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
-        if (err_host) CU(h, cudaMemcpyAsync(err_host + b0, base + oEr[j], sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st_out));
-        if (n_iter_host) CU(h, cudaMemcpyAsync(n_iter_host + b0, base + oNi[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        // the per-clip scalars go through pinned staging: a copy into the caller's (pageable) arrays would block this thread
+        // until the fit and the copy-out of this chunk are over, and nothing of the next chunk would be queued meanwhile
+        CU(h, cudaMemcpyAsync(stage_nb + b0, base + oNb[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        CU(h, cudaMemcpyAsync(stage_er + b0, base + oEr[j], sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        CU(h, cudaMemcpyAsync(stage_ni + b0, base + oNi[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        mark(oev, h->st_out);
         CU(h, cudaEventRecord(h->ev_out[j], h->st_out));
     }
     // drain all three streams whatever happened, so that no copy is in flight when the caller's buffers go away
+    if (trace) fprintf(stderr, "[ainmf host] all chunks enqueued at %.2f ms\n", since());
     cudaStreamSynchronize(h->st_in);
     cudaStreamSynchronize(h->st_cmp);
+    if (trace) fprintf(stderr, "[ainmf host] compute stream drained at %.2f ms\n", since());
     const cudaError_t e_out = cudaStreamSynchronize(h->st_out);
+    if (trace) {
+        fprintf(stderr, "[ainmf host] copy-out drained at %.2f ms\n", since());
+        auto at = [&](cudaEvent_t e) { float ms = 0.f; cudaEventElapsedTime(&ms, cev[0], e); return ms; };   // since the first copy-in began
+        for (size_t c = 0; 2 * c + 1 < tev.size(); ++c)
+            fprintf(stderr, "[ainmf host] chunk %zu on the device: copy-in %.2f-%.2f, fit %.2f-%.2f, copy-out %.2f-%.2f ms\n", c,
+                    at(cev[2 * c]), at(cev[2 * c + 1]), at(tev[2 * c]), at(tev[2 * c + 1]),
+                    2 * c + 1 < oev.size() ? at(oev[2 * c]) : 0.f, 2 * c + 1 < oev.size() ? at(oev[2 * c + 1]) : 0.f);
+        for (auto* v : {&tev, &cev, &oev}) for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    }
     if (rc == AINMF_OK && e_out != cudaSuccess) return fail(h, AINMF_ERR_CUDA, "copy-out: %s", cudaGetErrorString(e_out));
+    if (rc == AINMF_OK) {
+        if (n_bad_host) memcpy(n_bad_host, stage_nb, sizeof(int) * (size_t)p->batch);
+        if (err_host) memcpy(err_host, stage_er, sizeof(float) * (size_t)p->batch);
+        if (n_iter_host) memcpy(n_iter_host, stage_ni, sizeof(int) * (size_t)p->batch);
+    }
     return rc;
 }
 
