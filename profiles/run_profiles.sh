@@ -5,7 +5,7 @@
 TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-C4="--clips 64 --steps 1 --legs none --no-cpu-baseline"
+C4="--clips 148 --steps 1 --legs none --no-cpu-baseline"
 C5="--workload c5 --seconds 600 --steps 1 --no-cpu-baseline"
 KERN='(h_step_ts|xht_ts|w_side|w_finish|hbad|hbad_reduce|gather_rows|scatter_rows|build_perm|invert_flags|gram|reduce_splits|reduce_partials|stop|stft|istft|gap_mask|compact|colsum|colsum_reduce|fill|fill_rows|mean|init_w|init_h|finalize|err_reduce|transpose_h|unpack_w|numpy_normals|copy_indices|viol_sum|export_state|status_summary|count_not_done|range_mask|pass_through_all_bad)_kernel'
 python bench.py > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err || { echo "bench failed"; tail -20 $OUT/bench_${TAG}.err; exit 1; }
