@@ -202,7 +202,8 @@ struct NmfWork {
     float* kl_sums = nullptr;           // MU-KL: [2][B][KP] row sums of H, column sums of W (the denominators)
     double* kl_err = nullptr;           // MU-KL: [B] final divergence (kept across nmf_finalize, which reports the Frobenius error)
 };
-enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4 };
+enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4,
+       NMF_PHASE_STOP_PACKED = 8 };   // with STOP: the H-side violation is read from wk.h_viol_pack (summed hi + lo floats)
 void nmf_plan(int B, int T, int F, int KP, int n_sm, NmfWork* wk);
 size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk);
 // tensor-core path: build the TMA maps for problem `p` (after nmf_carve) and attach them; 0 on success

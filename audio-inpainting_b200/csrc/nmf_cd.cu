@@ -425,7 +425,7 @@ static __device__ double violation_in_reference_order(const float* __restrict__ 
 
 __global__ void __launch_bounds__(kThreads)
 stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, int nW,
-            const float* __restrict__ violH, int nH, const double* __restrict__ extra, int it, float tol,
+            const float* __restrict__ violH, int nH, const double* __restrict__ extra, const float* __restrict__ extra_pack, int it, float tol,
             const float* __restrict__ pgW, const float* __restrict__ pgH, int F, int T, int KP) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -435,7 +435,8 @@ stop_kernel(ClipState* __restrict__ st, int B, const float* __restrict__ violW, 
     for (int i = lane; i < nW; i += 32) v += (double)violW[(long long)b * nW + i];
     for (int i = lane; i < nH; i += 32) v += (double)violH[(long long)b * nH + i];
     v = warp_sum_d(v);
-    if (extra) v += extra[b];        // H-side violation already summed over the ranks (time-sharded mode)
+    if (extra_pack) v += (double)extra_pack[4 * b] + (double)extra_pack[4 * b + 1];   // time-sharded mode: the H-side violation summed
+    else if (extra) v += extra[b];                                                    // over the ranks (hi + lo floats, or a double)
     if (lane == 0) {
         ClipState s = st[b];
         if (pgW) {
@@ -735,7 +736,8 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     if (phases & NMF_PHASE_STOP) {
         prof_begin(PROF_STOP, s);
         AINMF_LAUNCH(stop_kernel, dim3(ceil_div(p.B, kThreads / 32)), dim3(kThreads), 0, s, p.state, p.B, wk.violW,
-                     wk.nW, wk.violH, wk.h_viol_sum ? 0 : wk.nH, (const double*)wk.h_viol_sum, it, p.tol,
+                     wk.nW, wk.violH, wk.h_viol_sum ? 0 : wk.nH, (const double*)wk.h_viol_sum,
+                     (phases & NMF_PHASE_STOP_PACKED) ? (const float*)wk.h_viol_pack : nullptr, it, p.tol,
                      (wk.exact_viol && !wk.h_viol_sum) ? wk.pgW : nullptr, wk.pgH, p.F, p.T, KP);
         e = cudaGetLastError();
         prof_end(PROF_STOP, s);

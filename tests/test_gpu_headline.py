@@ -90,7 +90,7 @@ def test_c5_shape_tensor_core_path_vs_oracle(ops, c5_case):
     check_against_oracle(x, y[0].cpu().numpy(), int(nb[0]), idx[0].cpu().numpy(), float(err[0]), int(nit[0]), yo, st, 2048, 512)
 
 
-def _sharded_worker(rank, world, port, out_dir, seconds, iters):
+def _sharded_worker(rank, world, port, out_dir, seconds, iters, tol=1e-4):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -138,7 +138,7 @@ def _sharded_worker(rank, world, port, out_dir, seconds, iters):
     N = len(x)
     from ainmf.sharding import shard_plan
     pl = shard_plan(N, 2048, 512, rank, world)
-    p = _capi.default_params(L, batch=1, n_samples=N, n_fft=2048, hop=512, rank=128, max_iter=iters, tol=1e-4, seed=0,
+    p = _capi.default_params(L, batch=1, n_samples=N, n_fft=2048, hop=512, rank=128, max_iter=iters, tol=tol, seed=0,
                              threshold=1e-4, frac_num=9, frac_den=10)
     nbytes = L.ainmf_sharded_workspace_bytes(h, C.byref(p))
     assert nbytes > 0
@@ -180,6 +180,29 @@ def test_c5_shape_time_sharded_two_ranks_vs_oracle(c5_case, tmp_path):
         n_bad, err, nit = int(d["nb"][0]), float(d["err"][0]), int(d["nit"][0])          # global values on every rank
     assert np.all(cover == 1)
     check_against_oracle(x, y, n_bad, None, err, nit, yo, st, 2048, 512)
+
+
+def test_c5_shape_time_sharded_early_stop_vs_oracle(ops, tmp_path):
+    """tol = 3e-3 stops sklearn at iteration 20 of 60 on this prefix.  The single-GPU tensor-core path and two time-sharded
+    ranks -- whose H-side violation travels with the NEXT iteration's exchange, the rule being evaluated one exchange late
+    and before any update -- must stop at the same iteration with the same objective and waveform."""
+    import torch.multiprocessing as mp
+    x = c5_prefix(100.0)
+    yo, st = libcalls.restore_columns(x, SR, n_fft=2048, hop=512, threshold=1e-4, frac=0.9, K=128, seed=0, max_iter=60, tol=3e-3,
+                                      return_all=True)
+    assert 1 < st["n_iter"] < 60
+    y1, idx, nb, W, H, err, nit = ops.nmf_inpaint(torch.from_numpy(x[None]).cuda(), 2048, 512, 128, 60, 3e-3, 0, 1e-4, 9, 10,
+                                                  -1, -1, 1, None, None)
+    check_against_oracle(x, y1[0].cpu().numpy(), int(nb[0]), idx[0].cpu().numpy(), float(err[0]), int(nit[0]), yo, st, 2048, 512)
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path), 100.0, 60, 3e-3), nprocs=2, join=True)
+    y = np.zeros(len(x), np.float32)
+    for r in range(2):
+        d = np.load(tmp_path / f"rank{r}.npz")
+        y[d["yb"]:d["ye"]] = d["y"]
+        n_bad, err2, nit2 = int(d["nb"][0]), float(d["err"][0]), int(d["nit"][0])
+        assert nit2 == st["n_iter"]
+    check_against_oracle(x, y, n_bad, None, err2, nit2, yo, st, 2048, 512)
 
 
 def test_c4_shape_random_fragment_clips_vs_oracle(ops):
