@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "comm.cu", "stft.cu", "mask.cu", "impute.cu", "nmf_cd.cu", "nmf_wside.cu", "nmf_mukl.cu", "nmf_small.cu", "rng.cu", "pcm.cu", "gaps.cu", "tc_host.cu", "nmf_tc.cu", "nmf_ts.cu"]
+SOURCES = ["api.cu", "comm.cu", "stft.cu", "mask.cu", "impute.cu", "nmf_cd.cu", "nmf_wside.cu", "nmf_mukl.cu", "nmf_coop.cu", "nmf_small.cu", "rng.cu", "pcm.cu", "gaps.cu", "tc_host.cu", "nmf_tc.cu", "nmf_ts.cu"]
 # diagnostics (descriptor probe, sweep unit test, tcgen05 issue-rate microbenchmark): their own library, loaded by
 # tests/ and tools/ only -- nothing of it is linked into or exported from the product library
 DIAG_SOURCES = ["diag/tc_probe.cu", "diag/sweep_test.cu", "diag/mma_bench.cu", "tc_host.cu"]

@@ -376,6 +376,13 @@ int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, in
     const bool kl = prob.solver == AINMF_SOLVER_MU_KL;
     const bool mu = prob.solver == AINMF_SOLVER_MU || kl;
     const int poll = mu ? 10 : 8;          // MU tests convergence every 10th iteration only
+    if (!mu && nmf_coop_eligible(prob, nw, h->n_sm) && !getenv("AINMF_NO_COOP")) {
+        // one clip: the whole fit is one cooperative launch, stop rule on the device, no polls (nmf_coop.cu)
+        prof_begin(PROF_H_STEP, s);                       // the profile's H-step slot times the whole fit (one launch)
+        CU(h, nmf_coop_fit(prob, nw, max_iter, h->n_sm, s));
+        prof_end(PROF_H_STEP, s);
+        return 0;
+    }
     if (mu && tol > 0.f) CU(h, kl ? nmf_mukl_begin(prob, nw, s) : nmf_mu_begin(prob, nw, s));
     if (tol > 0.f && !h->ev_poll[0])
         for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
@@ -803,11 +810,18 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     if (probe_ws == 0) return AINMF_ERR_INVALID;       // message set by make_plan
     const size_t per_clip_ws = (probe_ws + one.batch - 1) / one.batch;
     const long long N = p->n_samples;
+    const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256;
     if (max_device_bytes == 0) {
 #ifndef AINMF_EMU
-        size_t fr = 0, tot = 0;
-        CU(h, cudaMemGetInfo(&fr, &tot));
-        max_device_bytes = (size_t)((double)(fr + h->scratch_bytes) * 0.8);
+        // the scratch block of an earlier call that already holds this batch needs no query (cudaMemGetInfo costs 0.1-1 ms, a
+        // tenth of a single clip's whole restoration)
+        const size_t want = per_clip * (size_t)(p->batch < 512 ? p->batch : 512) * 5 / 4;
+        if (want <= h->scratch_bytes) max_device_bytes = h->scratch_bytes;
+        else {
+            size_t fr = 0, tot = 0;
+            CU(h, cudaMemGetInfo(&fr, &tot));
+            max_device_bytes = (size_t)((double)(fr + h->scratch_bytes) * 0.8);
+        }
 #else
         max_device_bytes = (size_t)1 << 30;
 #endif
@@ -816,7 +830,6 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
     // clips and, when the batch is large enough to be worth splitting, at most half the batch -- enough tiles per launch to
     // keep every SM busy for many rounds, small enough that only the first copy-in and the last copy-out are exposed.
-    const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256;
     long long chunk = (long long)(max_device_bytes / per_clip);
     if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
     if (chunk > 512) chunk = 512;

@@ -199,6 +199,7 @@ struct NmfWork {
     unsigned char* zero_flags = nullptr;  // [B][zero_stride] zeros: error evaluation that must not overwrite frames
     long long zero_stride = 0;
     int want_mu = 0;                    // set before nmf_work_bytes / nmf_carve: 1 = MU (Frobenius), 2 = MU (Kullback-Leibler)
+    char* coop_scratch = nullptr;       // 4 KB: grid-barrier word + per-CTA violation shares of the one-clip cooperative fit
     float* kl_sums = nullptr;           // MU-KL: [2][B][KP] row sums of H, column sums of W (the denominators)
     double* kl_err = nullptr;           // MU-KL: [B] final divergence (kept across nmf_finalize, which reports the Frobenius error)
 };
@@ -235,6 +236,10 @@ cudaError_t nmf_cd_phase(const NmfProblem& p, const NmfWork& wk, int it, int pha
 // nmf_wside.cu: the W half-step (w_side_kernel + w_finish_kernel); S = number of X.Ht partial buffers to sum
 cudaError_t launch_w_side(const NmfProblem& p, const NmfWork& wk, int S, cudaStream_t s);
 cudaError_t launch_set_err(ClipState* st, int B, const double* err_sq, cudaStream_t s);
+// ---- nmf_coop.cu: one spectrogram's whole fit as one cooperative persistent launch (all SMs, grid barriers between the
+// four phases of an iteration, stop rule on the device).  On return W / Ht hold the factors, state n_iter / viol / done.
+bool nmf_coop_eligible(const NmfProblem& p, const NmfWork& wk, int n_sm);
+cudaError_t nmf_coop_fit(const NmfProblem& p, const NmfWork& wk, int max_iter, int n_sm, cudaStream_t s);
 // ---- nmf_small.cu: a small spectrogram's whole fit -- and main4_NMF.py's chain of n_outer refits -- in one launch, one CTA
 // per clip, everything in shared memory (seeded initial factors).  bad: frames replaced by (W H)
 // after each fit.  On return Xt holds the restored frames, W / Ht the last fit's factors, state n_iter / err.

@@ -1017,6 +1017,7 @@ size_t nmf_work_bytes(int B, int T, int F, int KP, const NmfWork& wk) {
                        + al256(sizeof(float) * (size_t)B * wk.nW * KP) + 2 * al256(sizeof(float) * (size_t)B * KP) + al256(sizeof(float) * (size_t)B * wk.hbad_blocks * KP); // fill^T.W partials, bad-frame sums of Ht, fill^T.W, hbad shares
     n += al256(sizeof(float) * (size_t)B * wk.nW) + al256(sizeof(float) * (size_t)B * wk.nH);
     n += al256(sizeof(double) * (size_t)B * ceil_div(T, 16));
+    n += al256(4096);                                                             // coop_scratch
     if (wk.want_mu == 1) n += al256(sizeof(float) * (size_t)B * T * KP) + al256((size_t)B * round_up(T, 16));
     if (wk.want_mu == 2) n += al256(sizeof(float) * (size_t)B * 2 * KP) + al256(sizeof(double) * (size_t)B);
     if (wk.exact_viol) n += al256(sizeof(float) * (size_t)B * F * KP) + al256(sizeof(float) * (size_t)B * T * KP);
@@ -1048,6 +1049,7 @@ void nmf_carve(void* base, int B, int T, int F, int KP, NmfWork* wk) {
     wk->violW = (float*)take(sizeof(float) * (size_t)B * wk->nW);
     wk->violH = (float*)take(sizeof(float) * (size_t)B * wk->nH);
     wk->err_partial = (double*)take(sizeof(double) * (size_t)B * ceil_div(T, 16));
+    wk->coop_scratch = (char*)take(4096);
     if (wk->want_mu == 2) {
         wk->kl_sums = (float*)take(sizeof(float) * (size_t)B * 2 * KP);
         wk->kl_err = (double*)take(sizeof(double) * (size_t)B);

@@ -241,12 +241,48 @@ def test_tensor_core_path_skips_converged_clips(ops):
     W, H, err, nit = ops.nmf_fit(dev(X), K, 120, 2e-3, 7, None, None)
     nits = [int(v) for v in nit]
     assert min(nits) < max(nits), nits                                  # at least one clip stopped before another
-    for b in range(3):
-        Wb, Hb, eb, nb = ops.nmf_fit(dev(X[b:b + 1]), K, 120, 2e-3, 7, None, None)
-        assert int(nb[0]) == nits[b]
-        assert torch.equal(W[b], Wb[0]) and torch.equal(H[b], Hb[0]) and float(err[b]) == float(eb[0])
+    import os
+    os.environ["AINMF_NO_COOP"] = "1"           # one clip through the same batched kernels (not the cooperative one-clip launch)
+    try:
+        for b in range(3):
+            Wb, Hb, eb, nb = ops.nmf_fit(dev(X[b:b + 1]), K, 120, 2e-3, 7, None, None)
+            assert int(nb[0]) == nits[b]
+            assert torch.equal(W[b], Wb[0]) and torch.equal(H[b], Hb[0]) and float(err[b]) == float(eb[0])
+    finally:
+        os.environ.pop("AINMF_NO_COOP")
     Wo, Ho, no, eo = libcalls.nmf_fit(X[1], K, seed=7, max_iter=120, tol=2e-3)
     assert abs(nits[1] - no) <= 2 and abs(float(err[1]) - eo) <= 1e-3 * eo
+    # the same clip alone takes the cooperative launch (nmf_coop.cu: FFMA, stop rule on the device)
+    Wc, Hc, ec, nc = ops.nmf_fit(dev(X[1:2]), K, 120, 2e-3, 7, None, None)
+    assert abs(int(nc[0]) - no) <= 2 and abs(float(ec[0]) - eo) <= 1e-3 * eo
+
+
+@pytest.mark.parametrize("F,T,K,iters,tol", [(1025, 863, 40, 30, 0.0), (513, 1724, 64, 25, 0.0), (257, 431, 100, 20, 0.0),
+                                              (257, 500, 40, 300, 1e-3), (1025, 700, 128, 6, 0.0), (2049, 431, 64, 8, 0.0)])
+def test_cooperative_one_clip_fit_matches_sklearn(ops, F, T, K, iters, tol):
+    """One spectrogram = one cooperative launch (nmf_coop.cu): factors, objective and n_iter_ against sklearn's CD from the
+    same seed, on the c2 / c3 shapes, K = 40 ... 128, an early stop, n_fft = 4096; and the same factors as the general kernels give (AINMF_NO_COOP=1) within rounding."""
+    import os
+    rng = np.random.default_rng(F + T + K)
+    X = (np.abs(rng.standard_normal((F, 6))) @ np.abs(rng.standard_normal((6, T))) + 0.3 * np.abs(rng.standard_normal((F, T)))).astype(np.float32)
+    X[:, 40:60] = X[:, :20].mean(axis=1, keepdims=True)                     # identical columns, as an imputed gap has
+    Wo, Ho, no, eo = libcalls.nmf_fit(X, K, seed=3, max_iter=iters, tol=tol)
+    launches0 = __import__("ainmf")._lib.lib().ainmf_launch_count()
+    W, H, err, nit = ops.nmf_fit(dev(X[None]), K, iters, tol, 3, None, None)
+    torch.cuda.synchronize()
+    launches = __import__("ainmf")._lib.lib().ainmf_launch_count() - launches0
+    assert launches < 40, launches                                          # not the per-iteration kernels
+    assert abs(int(nit[0]) - no) <= (0 if tol == 0.0 else 1)
+    assert abs(float(err[0]) - eo) <= 1e-4 * eo
+    if tol == 0.0:
+        assert rel_l2(W[0].cpu().numpy(), Wo) < 2e-3 and rel_l2(H[0].cpu().numpy(), Ho) < 2e-3
+    os.environ["AINMF_NO_COOP"] = "1"
+    try:
+        W2, H2, err2, nit2 = ops.nmf_fit(dev(X[None]), K, iters, tol, 3, None, None)
+    finally:
+        os.environ.pop("AINMF_NO_COOP")
+    if tol == 0.0:                                                          # with a stop rule the tf32 path may stop an iteration apart
+        assert abs(float(err2[0]) - float(err[0])) <= 1e-4 * eo
 
 
 def test_nmf_objective_is_monotone(ops):
