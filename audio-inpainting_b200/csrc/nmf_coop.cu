@@ -344,51 +344,46 @@ nmf_coop_kernel(CoopParams p) {
 #define CO_TIC() do { if (dbg_on) c_t = clock64(); } while (0)
 #define CO_TOC(k) do { if (dbg_on) { const long long c_ = clock64(); c_ph[k] += c_ - c_t; c_t = c_; } } while (0)
     for (int it = 1; it <= p.max_iter; ++it) {
-        // ---- A: X.Ht for the own rows of W, this CTA's elements of Ht^T.Ht ----
-        CO_TIC();
-        switch (rpw) {
-            case 4: stream_products<KP, 1>(p.Ht, p.T, sXw, ring, sGp, gramH, dbg_on ? c_ph + 10 : nullptr); break;
-            case 8: stream_products<KP, 2>(p.Ht, p.T, sXw, ring, sGp, gramH, dbg_on ? c_ph + 10 : nullptr); break;
-            case 12: stream_products<KP, 3>(p.Ht, p.T, sXw, ring, sGp, gramH, dbg_on ? c_ph + 10 : nullptr); break;
-            default: stream_products<KP, 4>(p.Ht, p.T, sXw, ring, sGp, gramH, dbg_on ? c_ph + 10 : nullptr); break;
+        float v = 0.f;
+        // Two halves with the same code (one copy in the instruction cache): half 0 = A + B (stream Ht: X.Ht for the own rows
+        // of W and this CTA's elements of Ht^T.Ht; then the W sweep), half 1 = C + D (stream W: Xt.W for the own frames and the
+        // elements of W^T.W; then the H sweep).
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const float* other = half ? p.W : p.Ht;
+            const int n_other = half ? p.F : p.T;
+            const float* sX = half ? sXh : sXw;
+            const int rp = half ? rph : rpw;
+            float* gram = half ? gramW : gramH;
+            float* sOwn = half ? sH : sW;
+            const int n_own = half ? nt : nf;
+            float* gOwn = half ? p.Ht + (long long)t0 * KP : p.W + (long long)f0 * KP;
+            long long* tw = (dbg_on && half == 0) ? c_ph + 10 : nullptr;
+            CO_TIC();
+            switch (rp) {
+                case 4: stream_products<KP, 1>(other, n_other, sX, ring, sGp, gram, tw); break;
+                case 8: stream_products<KP, 2>(other, n_other, sX, ring, sGp, gram, tw); break;
+                case 12: stream_products<KP, 3>(other, n_other, sX, ring, sGp, gram, tw); break;
+                default: stream_products<KP, 4>(other, n_other, sX, ring, sGp, gram, tw); break;
+            }
+            CO_TOC(4 * half);
+            grid_barrier(p.bar, nb_ctas, bar_target);
+            CO_TOC(4 * half + 1);
+            gram_load<KP>(gram, sG, sInv);
+            v += sweep_rows<KP>(sOwn, ring, sG, sInv, n_own);
+            __syncthreads();
+            for (int i = tid; i < n_own * (KP / 4); i += kCoopThreads) {
+                const int r = i / (KP / 4), c = (i % (KP / 4)) * 4;
+                *reinterpret_cast<float4*>(gOwn + (long long)r * KP + c) = *reinterpret_cast<const float4*>(sOwn + r * AP + c);
+            }
+            if (half == 1) {
+                const double vd = block_sum_d((double)v, s_red);
+                if (tid == 0) p.viol_part[cta] = vd;
+            }
+            CO_TOC(4 * half + 2);
+            grid_barrier(p.bar, nb_ctas, bar_target);
+            CO_TOC(4 * half + 3);
         }
-        CO_TOC(0);
-        grid_barrier(p.bar, nb_ctas, bar_target);
-        CO_TOC(1);
-        // ---- B: W sweep ----
-        gram_load<KP>(gramH, sG, sInv);
-        float v = sweep_rows<KP>(sW, ring, sG, sInv, nf);
-        __syncthreads();
-        for (int i = tid; i < nf * (KP / 4); i += kCoopThreads) {
-            const int r = i / (KP / 4), c = (i % (KP / 4)) * 4;
-            *reinterpret_cast<float4*>(p.W + (long long)(f0 + r) * KP + c) = *reinterpret_cast<const float4*>(sW + r * AP + c);
-        }
-        CO_TOC(2);
-        grid_barrier(p.bar, nb_ctas, bar_target);
-        CO_TOC(3);
-        // ---- C: Xt.W for the own frames, this CTA's elements of W^T.W ----
-        switch (rph) {
-            case 4: stream_products<KP, 1>(p.W, p.F, sXh, ring, sGp, gramW); break;
-            case 8: stream_products<KP, 2>(p.W, p.F, sXh, ring, sGp, gramW); break;
-            case 12: stream_products<KP, 3>(p.W, p.F, sXh, ring, sGp, gramW); break;
-            default: stream_products<KP, 4>(p.W, p.F, sXh, ring, sGp, gramW); break;
-        }
-        CO_TOC(4);
-        grid_barrier(p.bar, nb_ctas, bar_target);
-        CO_TOC(5);
-        // ---- D: H sweep, violation share ----
-        gram_load<KP>(gramW, sG, sInv);
-        v += sweep_rows<KP>(sH, ring, sG, sInv, nt);
-        __syncthreads();
-        for (int i = tid; i < nt * (KP / 4); i += kCoopThreads) {
-            const int r = i / (KP / 4), c = (i % (KP / 4)) * 4;
-            *reinterpret_cast<float4*>(p.Ht + (long long)(t0 + r) * KP + c) = *reinterpret_cast<const float4*>(sH + r * AP + c);
-        }
-        const double vd = block_sum_d((double)v, s_red);
-        if (tid == 0) p.viol_part[cta] = vd;
-        CO_TOC(6);
-        grid_barrier(p.bar, nb_ctas, bar_target);
-        CO_TOC(7);
         // ---- stop rule: the same ordered sum in every CTA ----
         if (tid < 32) {
             double s = 0.0;

@@ -15,6 +15,15 @@ namespace ainmf {
 
 namespace {
 
+// packed fp32x2 FMA (sm_100a FFMA2: two lanes per issue slot); plain fmaf pairs in the CPU test harness
+__device__ __forceinline__ float2 kl_fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(AINMF_EMU)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
 constexpr float kEps32 = 1.1920929e-07f;      // np.finfo(np.float32).eps: sklearn's EPSILON
 constexpr int KL_TR = 64;                     // rows of the updated factor per block
 constexpr int KL_TC = 64;                     // columns (rows of the other factor) per chunk
@@ -95,21 +104,25 @@ kl_update_kernel(float* __restrict__ A, long long a_stride, int n_rows, const fl
         }
         __syncthreads();
         // first contraction: wh[i][j] = sum_k A[row i][k] * Bm[column j][k]
-        float wh[4][4];
+        float2 wh2[4][2];                                  // [row][column pair]: packed FFMA2
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) wh[i][j] = 0.f;
+        for (int i = 0; i < 4; ++i) { wh2[i][0] = make_float2(0.f, 0.f); wh2[i][1] = make_float2(0.f, 0.f); }
 #pragma unroll 4
         for (int k = 0; k < KP; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(sAT + k * PT + 4 * ty);
             const float4 c = *reinterpret_cast<const float4*>(sBT + k * PT + 4 * tx);
-            const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wh[i][j] = fmaf(av[i], cv[j], wh[i][j]);
+            for (int i = 0; i < 4; ++i) {
+                const float2 aa = make_float2(av[i], av[i]);
+                wh2[i][0] = kl_fma2(aa, c01, wh2[i][0]);
+                wh2[i][1] = kl_fma2(aa, c23, wh2[i][1]);
+            }
         }
+        float wh[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wh[i][0] = wh2[i][0].x; wh[i][1] = wh2[i][0].y; wh[i][2] = wh2[i][1].x; wh[i][3] = wh2[i][1].y; }
         if (MODE == 2) {
             // x > eps: x log(x / max(wh, eps)) - x; every element of the matrix: + wh (the sum of W.H)
 #pragma unroll
@@ -154,9 +167,14 @@ kl_update_kernel(float* __restrict__ A, long long a_stride, int n_rows, const fl
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+                const float2 rr2 = make_float2(rv[i], rv[i]);
 #pragma unroll
-                for (int q = 0; q < KQ; ++q) acc[i][q] = fmaf(rv[i], bv[q], acc[i][q]);
+                for (int q = 0; q < KQ; q += 2) {
+                    const float2 t2 = kl_fma2(rr2, make_float2(bv[q], bv[q + 1]), make_float2(acc[i][q], acc[i][q + 1]));
+                    acc[i][q] = t2.x; acc[i][q + 1] = t2.y;
+                }
+            }
         }
     }
     if (MODE == 2) {
