@@ -93,6 +93,8 @@ template <int KP, int RQ>                      // RQ = rpp / 4: quads of rows (c
 __device__ __forceinline__ void stream_products(const float* __restrict__ Other, int n, const float* __restrict__ sX,
                                                 float* __restrict__ ring, float* __restrict__ sGp, float* __restrict__ gram_out, long long* tw = nullptr) {
     constexpr int rpp = 4 * RQ;
+    long long qa = 0;
+    if (tw) qa = clock64();
     using Cfg = CoopCfg<KP>;
     constexpr int CH = Cfg::CH, SF = Cfg::STAGE_FLOATS, KQ = Cfg::KQ, NJ = Cfg::NJ, WG = Cfg::WG, NJR = Cfg::NJR, GE = Cfg::GE,
                   RG = kCoopThreads / GE;
@@ -122,11 +124,13 @@ __device__ __forceinline__ void stream_products(const float* __restrict__ Other,
             if (tid + k * kCoopThreads < n16)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + k * (16u * kCoopThreads)), "l"(src + k * (4 * kCoopThreads)) : "memory");
     };
+    if (tw) { const long long qb = clock64(); tw[6] += qb - qa; qa = qb; }
 #pragma unroll
     for (int c = 0; c < Cfg::STAGES - 1; ++c) {
         if (c < nch) issue(c);
         cp_async_commit();
     }
+    if (tw) { const long long qb = clock64(); tw[7] += qb - qa; }
     for (int c = 0; c < nch; ++c) {
         long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
         if (tw) q0 = clock64();
@@ -339,7 +343,7 @@ nmf_coop_kernel(CoopParams p) {
     int n_iter = 0, done = 0;
     float* gramH = p.gram;
     float* gramW = p.gram + KP * KP;
-    long long c_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, c_t = 0;
+    long long c_ph[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, c_t = 0;
     const bool dbg_on = p.dbg != nullptr && tid == 0 && cta == 0;
 #define CO_TIC() do { if (dbg_on) c_t = clock64(); } while (0)
 #define CO_TOC(k) do { if (dbg_on) { const long long c_ = clock64(); c_ph[k] += c_ - c_t; c_t = c_; } } while (0)
@@ -400,7 +404,7 @@ nmf_coop_kernel(CoopParams p) {
         if (viol_init == 0.0 || tot / viol_init <= (double)p.tol) { done = 1; break; }
         // (the next write of viol_part is three barriers away)
     }
-    if (dbg_on) for (int i = 0; i < 16; ++i) p.dbg[i] = (i == 9) ? n_iter : c_ph[i];
+    if (dbg_on) for (int i = 0; i < 20; ++i) p.dbg[i] = (i == 9) ? n_iter : c_ph[i];
     if (cta == 0 && tid == 0) {
         ClipState s = p.st[0];
         s.n_iter = n_iter; s.viol_init = viol_init; s.viol_last = viol_last; s.done = done;
@@ -441,15 +445,15 @@ cudaError_t coop_launch(const NmfProblem& p, const NmfWork& wk, int max_iter, in
     e = cudaLaunchCooperativeKernel((const void*)kern, dim3(n_sm), dim3(kCoopThreads), args, smem, s);
     if (dbg_left > 0 && e == cudaSuccess) {
         --dbg_left;
-        long long hb[16];
+        long long hb[20];
         cudaStreamSynchronize(s);
         cudaMemcpy(hb, cp.dbg, sizeof hb, cudaMemcpyDeviceToHost);
         const char* nm[9] = {"A stream Ht", "barrier 1", "B G+sweep+store", "barrier 2", "C stream W", "barrier 3", "D G+sweep+store+viol", "barrier 4", "stop sum"};
         const double n = hb[9] > 0 ? (double)hb[9] : 1.0;
         fprintf(stderr, "[coop-debug F=%d T=%d KP=%d rows %d/%d smem %zu] CTA 0, %lld iterations, cycles per iteration:", p.F, p.T, KP, cp.rows_w, cp.rows_h, smem, hb[9]);
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f;", nm[i], hb[i] / n);
-        fprintf(stderr, " [A per iteration: issue %.0f, cp.async wait %.0f, barrier %.0f, arithmetic %.0f, barrier %.0f, sums after the stream %.0f]\n",
-                hb[10] / n, hb[11] / n, hb[12] / n, hb[13] / n, hb[14] / n, hb[15] / n);
+        fprintf(stderr, " [A per iteration: issue %.0f, cp.async wait %.0f, barrier %.0f, arithmetic %.0f, barrier %.0f, sums after the stream %.0f, setup %.0f, first issues %.0f]\n",
+                hb[10] / n, hb[11] / n, hb[12] / n, hb[13] / n, hb[14] / n, hb[15] / n, hb[16] / n, hb[17] / n);
     }
     return e;
 }
