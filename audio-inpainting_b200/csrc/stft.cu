@@ -29,9 +29,10 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
     const int seg_len = (kStftFramesPerBlock - 1) * hop + n_fft;
     float2* s_twh = reinterpret_cast<float2*>(smem_raw);          // [M]
     float2* s_twf = s_twh + M;                                     // [M + 1] (+1 pad to keep 16B alignment below)
-    float2* s_a = s_twf + (M + 2);                                 // [FP][M]
-    float2* s_b = s_a + kStftFramesPerPass * M;                    // [FP][M]
-    float* s_win = reinterpret_cast<float*>(s_b + kStftFramesPerPass * M);   // [n_fft]
+    const int MP = fft_pitch(M), ps = fft_pad_shift(M);
+    float2* s_a = s_twf + (M + 2);                                 // [FP][MP] (padded layout of fft.cuh)
+    float2* s_b = s_a + kStftFramesPerPass * MP;                   // [FP][MP]
+    float* s_win = reinterpret_cast<float*>(s_b + kStftFramesPerPass * MP);  // [n_fft]
     float* s_seg = s_win + n_fft;                                  // [seg_len]
 
     const int b = blockIdx.y;
@@ -55,7 +56,7 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
         for (int idx = threadIdx.x; idx < kStftFramesPerPass * M; idx += blockDim.x) {
             const int q = idx >> lM, j = idx & (M - 1);
             const float* fr = s_seg + (fbase + q) * hop;
-            s_a[idx] = make_float2(fr[2 * j] * s_win[2 * j], fr[2 * j + 1] * s_win[2 * j + 1]);
+            s_a[q * MP + fft_pad(j, ps)] = make_float2(fr[2 * j] * s_win[2 * j], fr[2 * j + 1] * s_win[2 * j + 1]);
         }
         __syncthreads();
         const float2* Zh = block_fft_forward(s_a, s_b, s_twh, M, kStftFramesPerPass);
@@ -67,9 +68,9 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
             float2 X = make_float2(0.f, 0.f);
             float mag = 0.f;
             if (k < F) {
-                const float2* zq = Zh + q * M;
-                const float2 za = zq[k & (M - 1)];
-                const float2 zb = zq[(M - k) & (M - 1)];
+                const float2* zq = Zh + q * MP;
+                const float2 za = zq[fft_pad(k & (M - 1), ps)];
+                const float2 zb = zq[fft_pad((M - k) & (M - 1), ps)];
                 const float2 E = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
                 const float2 O = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));
                 const float2 t = cmul(s_twf[k], O);
@@ -87,7 +88,7 @@ stft_kernel(const float* __restrict__ x, long long x_stride, long long x_origin,
 
 static size_t stft_smem_bytes(int n_fft, int hop) {
     const int M = n_fft / 2;
-    return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * M) +
+    return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * fft_pitch(M)) +
            sizeof(float) * (size_t)(n_fft + (kStftFramesPerBlock - 1) * hop + n_fft);
 }
 
@@ -124,9 +125,10 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
     const int tile = kIstftHopsPerBlock * hop;
     float2* s_twh = reinterpret_cast<float2*>(smem_raw);          // [M]
     float2* s_twf = s_twh + M;                                     // [M + 1]
-    float2* s_a = s_twf + (M + 2);                                 // [FP][M]
-    float2* s_b = s_a + kStftFramesPerPass * M;                    // [FP][M]
-    float* s_win = reinterpret_cast<float*>(s_b + kStftFramesPerPass * M);   // [n_fft]
+    const int MP = fft_pitch(M), ps = fft_pad_shift(M);
+    float2* s_a = s_twf + (M + 2);                                 // [FP][MP] (padded layout of fft.cuh)
+    float2* s_b = s_a + kStftFramesPerPass * MP;                   // [FP][MP]
+    float* s_win = reinterpret_cast<float*>(s_b + kStftFramesPerPass * MP);  // [n_fft]
     float* s_out = s_win + n_fft;                                  // [tile]
 
     const int b = blockIdx.y;
@@ -208,7 +210,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
                 // Zk = E + i*O ; store conj(Zk)
                 out = make_float2(E.x - O.y, -(E.y + O.x));
             }
-            s_a[idx] = out;
+            s_a[q * MP + fft_pad(k, ps)] = out;
         }
         __syncthreads();
         const float2* zt = block_fft_forward(s_a, s_b, s_twh, M, kStftFramesPerPass);
@@ -220,7 +222,7 @@ istft_kernel(const float* __restrict__ V, const float2* __restrict__ Z, long lon
                 for (int j = threadIdx.x; j < n_fft; j += blockDim.x) {
                     const int p = base + j;
                     if (p >= 0 && p < tile) {
-                        const float2 z = zt[q * M + (j >> 1)];
+                        const float2 z = zt[q * MP + fft_pad(j >> 1, ps)];
                         float v = (j & 1) ? -z.y : z.x;
                         v = (v * inv_M) * win_sum;
                         s_out[p] += v * s_win[j];
@@ -251,7 +253,7 @@ size_t stft_smem_need(int n_fft, int hop, bool forward, bool inverse) {
 }
 static size_t istft_smem_bytes(int n_fft, int hop) {
     const int M = n_fft / 2;
-    return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * M) +
+    return sizeof(float2) * (size_t)(M + (M + 2) + 2 * kStftFramesPerPass * fft_pitch(M)) +
            sizeof(float) * (size_t)(n_fft + kIstftHopsPerBlock * hop);
 }
 

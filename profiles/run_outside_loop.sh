@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
-ARGS="--steps 1 --warmup 3 --no-cpu-baseline"
+ARGS="--steps 1 --warmup 3 --no-cpu-baseline --legs none"
 python bench.py $ARGS > $OUT/plain_outside_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none \
     -k regex:'(stft|istft|gap_mask|range_mask|compact|colsum|colsum_reduce|fill|fill_rows|mean|init_w|init_h|invert_flags|build_perm|gather_rows|scatter_rows|export_state|unpack_factors|unpack_w|transpose_h|finalize|err_reduce)_kernel' \
