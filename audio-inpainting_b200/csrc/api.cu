@@ -828,24 +828,38 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     }
     // Clips go through in chunks, two in flight: while chunk c is being fitted, chunk c+1 arrives on the copy-in stream and
     // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
-    // clips and, when the batch is large enough to be worth splitting, at most half the batch -- enough tiles per launch to
-    // keep every SM busy for many rounds, small enough that only the first copy-in and the last copy-out are exposed.
+    // clips (and what device memory allows).
     long long chunk = (long long)(max_device_bytes / per_clip);
     if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
     if (chunk > 512) chunk = 512;
     if (chunk > p->batch) chunk = p->batch;
-    // The persistent kernels hand out (clip, tile) items to one CTA per SM, every item the same size: a chunk of n_sm clips
-    // (or a multiple) fills every round of every kernel exactly, so splitting a batch into such chunks costs no extra
-    // rounds, and with ~4 chunks only the first quarter's copy-in and the last (short) chunk's copy-out stay exposed.
-    if (p->batch >= 2 * h->n_sm) {
-        long long m = (p->batch / 4) / h->n_sm;
-        if (m < 1) m = 1;
-        if (m * h->n_sm < chunk) chunk = m * h->n_sm;
-        else if (chunk >= h->n_sm) chunk = chunk / h->n_sm * h->n_sm;
-    }
-    if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk
-        const long long v = atoll(ev);
-        if (v >= 1 && v < chunk) chunk = v;
+    // Chunk schedule.  A chunk costs a fixed ~30 us per iteration (launch gaps, fill and drain of six kernels) whatever its
+    // size, so few large chunks beat many small ones; what stays exposed is the copy-in of the first chunk and the copy-out
+    // of the last.  So: a first chunk of n_sm clips (one clip per SM in every round of the persistent kernels, the smallest
+    // size that still runs at ~95 % of the large-batch rate; 4.7 ms of copy-in at 10 s clips), then the rest in equal
+    // chunks as large as memory and the 512-clip cap allow.  512 clips: [148, 364], 4096: [148, 8 x 493.5].
+    std::vector<long long> c_begin;          // first clip of every chunk, then the batch size
+    {
+        long long first = chunk;
+        if (p->batch >= 2 * h->n_sm && chunk >= 2 * h->n_sm) first = h->n_sm;
+        if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk, all equal
+            const long long v = atoll(ev);
+            if (v >= 1 && v < chunk) first = chunk = v;
+        }
+        if (const char* ev = getenv("AINMF_HOST_FIRST")) {      // development switch: clips in the first chunk
+            const long long v = atoll(ev);
+            if (v >= 1 && v <= chunk) first = v;
+        }
+        c_begin.push_back(0);
+        long long done = first < p->batch ? first : p->batch;
+        c_begin.push_back(done);
+        const long long rest = p->batch - done;
+        if (rest > 0) {
+            const long long n = (rest + chunk - 1) / chunk;
+            for (long long i = 1; i <= n; ++i) c_begin.push_back(done + rest * i / n);
+        }
+        chunk = 0;
+        for (size_t i = 0; i + 1 < c_begin.size(); ++i) if (c_begin[i + 1] - c_begin[i] > chunk) chunk = c_begin[i + 1] - c_begin[i];
     }
     ainmf_params cp = *p;
     cp.batch = (int32_t)chunk;
@@ -877,8 +891,8 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     int* stage_nb = (int*)pin;
     float* stage_er = (float*)(stage_nb + p->batch);
     int* stage_ni = (int*)(stage_er + p->batch);
-    const long long n_chunks = (p->batch + chunk - 1) / chunk;
-    auto chunk_size = [&](long long c) { const long long b0 = c * chunk; return (int)((p->batch - b0 < chunk) ? p->batch - b0 : chunk); };
+    const long long n_chunks = (long long)c_begin.size() - 1;
+    auto chunk_size = [&](long long c) { return (int)(c_begin[c + 1] - c_begin[c]); };
     const bool trace = getenv("AINMF_HOST_TRACE") != nullptr;   // host wall-clock of the phases, device time of every chunk's copies and fit
     std::vector<cudaEvent_t> tev, cev;
     auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); } };
@@ -886,7 +900,7 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         const int j = (int)(c & 1);
         if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_in, h->ev_done[j], 0));       // the fit of chunk c-2 has read this x buffer
         mark(cev, h->st_in);
-        CU(h, cudaMemcpyAsync(base + oX[j], x_host + c * chunk * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
+        CU(h, cudaMemcpyAsync(base + oX[j], x_host + c_begin[c] * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
         mark(cev, h->st_in);
         CU(h, cudaEventRecord(h->ev_in[j], h->st_in));
         return 0;
@@ -899,7 +913,7 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     for (long long c = 0; c < n_chunks && rc == AINMF_OK; ++c) {
         if (trace) fprintf(stderr, "[ainmf host] chunk %lld: enqueue starts at %.2f ms\n", c, since());
         const int j = (int)(c & 1), nb = chunk_size(c);
-        const long long b0 = c * chunk;
+        const long long b0 = c_begin[c];
         if (c + 1 < n_chunks && (rc = copy_in(c + 1))) break;                      // enqueued before the fit blocks this thread at its polls
         cp.batch = nb;
         CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_in[j], 0));

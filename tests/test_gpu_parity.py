@@ -497,7 +497,7 @@ def test_host_entry_point_pipelines_chunks_and_matches_the_device_op(ops):
     same frame counts and iteration counts, objective within 1e-5, waveform within 90 dB (the kernels pick their split
     factors from the batch size, so the floating-point summation order differs between a 300-clip and a 150-clip launch;
     a lost dependency between the three streams would show up as garbage, not as 1e-6) -- for the default split
-    (300 clips -> 150 + 150) and for a memory cap that forces many small chunks with buffer reuse."""
+    (300 clips -> 148 + 152) and for a memory cap that forces many small chunks with buffer reuse."""
     import ctypes as C
     import ainmf
     from ainmf import _capi
@@ -519,7 +519,7 @@ def test_host_entry_point_pipelines_chunks_and_matches_the_device_op(ops):
                              threshold=1e-4, frac_num=9, frac_den=10)
     xh = torch.from_numpy(X).pin_memory()
     ydn, errn = yd.cpu().numpy(), errd.cpu().numpy()
-    for cap in (0, 40 << 20):                            # default chunking (150 + 150); 40 MB cap -> many chunks, buffers reused
+    for cap in (0, 40 << 20):                            # default chunking (148 + 152); 40 MB cap -> many chunks, buffers reused
         yh = torch.zeros((B, N), dtype=torch.float32).pin_memory()
         nb, er, ni = np.zeros(B, np.int32), np.zeros(B, np.float32), np.zeros(B, np.int32)
         rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), nb.ctypes.data_as(C.c_void_p),

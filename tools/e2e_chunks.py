@@ -27,8 +27,9 @@ nbh = np.zeros(B, np.int32); errh = np.zeros(B, np.float32); nih = np.zeros(B, n
 p = _capi.default_params(L, batch=B, n_samples=N, n_fft=wl["n_fft"], hop=wl["hop"], rank=K, max_iter=200, tol=1e-4,
                          seed=wl["seed"], threshold=wl["thr"], frac_num=wl["num"], frac_den=wl["den"])
 for ch in sys.argv[1:] or ["512", "296", "148", "74", "0"]:
-    if ch == "0": os.environ.pop("AINMF_HOST_CHUNK", None)
-    else: os.environ["AINMF_HOST_CHUNK"] = ch
+    os.environ.pop("AINMF_HOST_CHUNK", None); os.environ.pop("AINMF_HOST_FIRST", None)
+    if ch.startswith("f"): os.environ["AINMF_HOST_FIRST"] = ch[1:]        # fN: first chunk of N clips, the rest as by default
+    elif ch != "0": os.environ["AINMF_HOST_CHUNK"] = ch
     def step():
         rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), nbh.ctypes.data_as(C.c_void_p),
                                   errh.ctypes.data_as(C.c_void_p), nih.ctypes.data_as(C.c_void_p), 0)
