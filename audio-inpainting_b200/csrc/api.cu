@@ -801,6 +801,7 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
                        float* err_host, int32_t* n_iter_host, size_t max_device_bytes) {
     if (!h) return AINMF_ERR_INVALID;
     if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
+    const auto t_call = std::chrono::steady_clock::now();
     CU(h, cudaSetDevice(h->device));
     // workspace per clip, estimated on a batch large enough to include what only big batches allocate (the permuted copy
     // of the spectrogram for the good-first frame order)
@@ -811,13 +812,59 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     const size_t per_clip_ws = (probe_ws + one.batch - 1) / one.batch;
     const long long N = p->n_samples;
     const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256;
+    // Clips go through in chunks, two in flight: while chunk c is being fitted, chunk c+1 arrives on the copy-in stream and
+    // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
+    // clips (and what device memory allows).
+    // Chunk schedule.  A chunk costs a fixed ~8 ms (200 iterations x launch gaps, fill and drain of six kernels) whatever its
+    // size, so few large chunks beat many small ones; what stays exposed is the copy-in of the first chunk and the copy-out
+    // of the last.  So: a first chunk of n_sm clips (one clip per SM in every round of the persistent kernels, the smallest
+    // size that still runs at ~95 % of the large-batch rate; 4.7 ms of copy-in at 10 s clips), then the rest in equal
+    // chunks as large as memory and the 512-clip cap allow.  512 clips: [148, 364] (measured against [148, 148, 148, 68],
+    // [148, 216, 148], [148, 296, 68], [222, 290], [296, 216], [74, 438]: profiles/r02e_e2e_chunk_schedules.txt).
+    std::vector<long long> c_begin;          // first clip of every chunk, then the batch size
+    long long chunk = 0;                     // clips in the largest chunk
+    ainmf_params cp = *p;
+    size_t ws = 0, o = 0, oX[2], oY[2], oNb[2], oEr[2], oNi[2], oWs = 0;
+    auto schedule = [&](long long cap) {     // chunks of at most cap clips, and the scratch layout that holds them
+        if (cap > 512) cap = 512;
+        if (cap > p->batch) cap = p->batch;
+        long long first = cap;
+        if (p->batch >= 2 * h->n_sm && cap >= 2 * h->n_sm) first = h->n_sm;
+        if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk, all equal
+            const long long v = atoll(ev);
+            if (v >= 1 && v < cap) first = cap = v;
+        }
+        if (const char* ev = getenv("AINMF_HOST_FIRST")) {      // development switch: clips in the first chunk
+            const long long v = atoll(ev);
+            if (v >= 1 && v <= cap) first = v;
+        }
+        c_begin.clear();
+        c_begin.push_back(0);
+        const long long done = first < p->batch ? first : p->batch;
+        c_begin.push_back(done);
+        if (p->batch > done) {
+            const long long rest = p->batch - done, n = (rest + cap - 1) / cap;
+            for (long long i = 1; i <= n; ++i) c_begin.push_back(done + rest * i / n);
+        }
+        chunk = 0;
+        for (size_t i = 0; i + 1 < c_begin.size(); ++i) if (c_begin[i + 1] - c_begin[i] > chunk) chunk = c_begin[i + 1] - c_begin[i];
+        cp.batch = (int32_t)chunk;
+        ws = ainmf_workspace_bytes(h, &cp);
+        o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+        for (int i = 0; i < 2; ++i) {
+            oX[i] = take(sizeof(float) * chunk * N); oY[i] = take(sizeof(float) * chunk * N);
+            oNb[i] = take(sizeof(int) * chunk); oEr[i] = take(sizeof(float) * chunk); oNi[i] = take(sizeof(int) * chunk);
+        }
+        oWs = take(ws);
+    };
     if (max_device_bytes == 0) {
 #ifndef AINMF_EMU
-        // the scratch block of an earlier call that already holds this batch needs no query (cudaMemGetInfo costs 0.1-1 ms, a
-        // tenth of a single clip's whole restoration)
-        const size_t want = per_clip * (size_t)(p->batch < 512 ? p->batch : 512) * 5 / 4;
-        if (want <= h->scratch_bytes) max_device_bytes = h->scratch_bytes;
-        else {
+        // No cap given: plan for the 512-clip cap; only if the scratch block of an earlier call does not already hold that
+        // layout is the free memory queried (cudaMemGetInfo is not cheap: 0.2 ms most of the time, 15-75 ms every fourth
+        // call or so on the measured boxes -- up to a quarter of a 512-clip call).
+        schedule(512);
+        if (o > h->scratch_bytes) {
             size_t fr = 0, tot = 0;
             CU(h, cudaMemGetInfo(&fr, &tot));
             max_device_bytes = (size_t)((double)(fr + h->scratch_bytes) * 0.8);
@@ -826,52 +873,11 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         max_device_bytes = (size_t)1 << 30;
 #endif
     }
-    // Clips go through in chunks, two in flight: while chunk c is being fitted, chunk c+1 arrives on the copy-in stream and
-    // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
-    // clips (and what device memory allows).
-    long long chunk = (long long)(max_device_bytes / per_clip);
-    if (chunk < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
-    if (chunk > 512) chunk = 512;
-    if (chunk > p->batch) chunk = p->batch;
-    // Chunk schedule.  A chunk costs a fixed ~30 us per iteration (launch gaps, fill and drain of six kernels) whatever its
-    // size, so few large chunks beat many small ones; what stays exposed is the copy-in of the first chunk and the copy-out
-    // of the last.  So: a first chunk of n_sm clips (one clip per SM in every round of the persistent kernels, the smallest
-    // size that still runs at ~95 % of the large-batch rate; 4.7 ms of copy-in at 10 s clips), then the rest in equal
-    // chunks as large as memory and the 512-clip cap allow.  512 clips: [148, 364], 4096: [148, 8 x 493.5].
-    std::vector<long long> c_begin;          // first clip of every chunk, then the batch size
-    {
-        long long first = chunk;
-        if (p->batch >= 2 * h->n_sm && chunk >= 2 * h->n_sm) first = h->n_sm;
-        if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk, all equal
-            const long long v = atoll(ev);
-            if (v >= 1 && v < chunk) first = chunk = v;
-        }
-        if (const char* ev = getenv("AINMF_HOST_FIRST")) {      // development switch: clips in the first chunk
-            const long long v = atoll(ev);
-            if (v >= 1 && v <= chunk) first = v;
-        }
-        c_begin.push_back(0);
-        long long done = first < p->batch ? first : p->batch;
-        c_begin.push_back(done);
-        const long long rest = p->batch - done;
-        if (rest > 0) {
-            const long long n = (rest + chunk - 1) / chunk;
-            for (long long i = 1; i <= n; ++i) c_begin.push_back(done + rest * i / n);
-        }
-        chunk = 0;
-        for (size_t i = 0; i + 1 < c_begin.size(); ++i) if (c_begin[i + 1] - c_begin[i] > chunk) chunk = c_begin[i + 1] - c_begin[i];
+    if (max_device_bytes != 0) {
+        const long long cap = (long long)(max_device_bytes / per_clip);
+        if (cap < 1) return fail(h, AINMF_ERR_WORKSPACE, "one clip needs %zu bytes of device memory", per_clip);
+        schedule(cap);
     }
-    ainmf_params cp = *p;
-    cp.batch = (int32_t)chunk;
-    const size_t ws = ainmf_workspace_bytes(h, &cp);
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
-    size_t oX[2], oY[2], oNb[2], oEr[2], oNi[2];
-    for (int i = 0; i < 2; ++i) {
-        oX[i] = take(sizeof(float) * chunk * N); oY[i] = take(sizeof(float) * chunk * N);
-        oNb[i] = take(sizeof(int) * chunk); oEr[i] = take(sizeof(float) * chunk); oNi[i] = take(sizeof(int) * chunk);
-    }
-    const size_t oWs = take(ws);
     void* scr;
     int rc = get_scratch(h, o, &scr);
     if (rc) return rc;
@@ -936,7 +942,8 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         CU(h, cudaEventRecord(h->ev_out[j], h->st_out));
     }
     // drain all three streams whatever happened, so that no copy is in flight when the caller's buffers go away
-    if (trace) fprintf(stderr, "[ainmf host] all chunks enqueued at %.2f ms\n", since());
+    const double t_enq = since();
+    if (trace) fprintf(stderr, "[ainmf host] all chunks enqueued at %.2f ms\n", t_enq);
     cudaStreamSynchronize(h->st_in);
     cudaStreamSynchronize(h->st_cmp);
     if (trace) fprintf(stderr, "[ainmf host] compute stream drained at %.2f ms\n", since());
@@ -950,6 +957,9 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
                     2 * c + 1 < oev.size() ? at(oev[2 * c]) : 0.f, 2 * c + 1 < oev.size() ? at(oev[2 * c + 1]) : 0.f);
         for (auto* v : {&tev, &cev, &oev}) for (cudaEvent_t e : *v) cudaEventDestroy(e);
     }
+    if (getenv("AINMF_HOST_TIMES"))      // one line per call: where the host spent it
+        fprintf(stderr, "[ainmf host] setup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+                std::chrono::duration<double, std::milli>(t_entry - t_call).count(), t_enq, since() - t_enq);
     if (rc == AINMF_OK && e_out != cudaSuccess) return fail(h, AINMF_ERR_CUDA, "copy-out: %s", cudaGetErrorString(e_out));
     if (rc == AINMF_OK) {
         if (n_bad_host) memcpy(n_bad_host, stage_nb, sizeof(int) * (size_t)p->batch);

@@ -28,16 +28,16 @@ p = _capi.default_params(L, batch=B, n_samples=N, n_fft=wl["n_fft"], hop=wl["hop
                          seed=wl["seed"], threshold=wl["thr"], frac_num=wl["num"], frac_den=wl["den"])
 for ch in sys.argv[1:] or ["512", "296", "148", "74", "0"]:
     os.environ.pop("AINMF_HOST_CHUNK", None); os.environ.pop("AINMF_HOST_FIRST", None)
-    if ch.startswith("f"): os.environ["AINMF_HOST_FIRST"] = ch[1:]        # fN: first chunk of N clips, the rest as by default
+    if ch.startswith("f"): os.environ["AINMF_HOST_FIRST"] = ch[1:]      # fN: first chunk of N clips, the rest as by default
     elif ch != "0": os.environ["AINMF_HOST_CHUNK"] = ch
     def step():
         rc = L.ainmf_inpaint_host(h, C.byref(p), C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()), nbh.ctypes.data_as(C.c_void_p),
                                   errh.ctypes.data_as(C.c_void_p), nih.ctypes.data_as(C.c_void_p), 0)
         ainmf._lib.check(rc, 0)
     for _ in range(2): step()
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(3): step()
+    torch.cuda.synchronize(); t0 = time.perf_counter(); each = []
+    for _ in range(3): t1 = time.perf_counter(); step(); each.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
-    print(f"e2e chunk {ch}: {dt*1e3:.1f} ms", flush=True)
+    print(f"e2e chunk {ch}: {dt*1e3:.1f} ms  (calls: {', '.join('%.1f' % e for e in each)})", flush=True)
     if os.environ.get("TRACE_ONE"):
         os.environ["AINMF_HOST_TRACE"] = "1"; step(); torch.cuda.synchronize(); os.environ.pop("AINMF_HOST_TRACE")
