@@ -111,6 +111,8 @@ struct ainmf_context {
     size_t pinned_bytes = 0;
     int* poll_host = nullptr;     // pinned
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};   // stop-flag polls, one group of iterations behind the launches
+    cudaStream_t st_aux = nullptr;                 // side stream of the iteration (hbad next to the X.Ht kernel) and its fork / join events
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // ainmf_inpaint_host pipeline: copy-in / compute / copy-out streams and the events that order two chunks in flight
     cudaStream_t st_in = nullptr, st_cmp = nullptr, st_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -386,11 +388,20 @@ int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, in
     if (mu && tol > 0.f) CU(h, kl ? nmf_mukl_begin(prob, nw, s) : nmf_mu_begin(prob, nw, s));
     if (tol > 0.f && !h->ev_poll[0])
         for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
+    NmfWork nwf = nw;                      // with the side stream for the reductions that run next to the X.Ht kernel
+    if (!mu && nw.use_tc && prob.t_good && !getenv("AINMF_NO_AUX_STREAM")) {
+        if (!h->st_aux) {
+            CU(h, cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking));
+            CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        nwf.aux_stream = h->st_aux; nwf.ev_fork = h->ev_fork; nwf.ev_join = h->ev_join;
+    }
     int pending = -1;
     for (int it = 1; it <= max_iter; ++it) {
         if (kl) CU(h, nmf_mukl_iterate(prob, nw, it, s));
         else if (mu) CU(h, nmf_mu_iterate(prob, nw, it, s));
-        else CU(h, nmf_cd_iterate(prob, nw, it, s));
+        else CU(h, nmf_cd_iterate(prob, nwf, it, s));
         if (tol > 0.f && (it % poll == 0) && it < max_iter) {
             const int g = (it / poll) & 1;
             int* d_out = d_flag + (g ? 3 : 0);
@@ -467,6 +478,7 @@ int ainmf_destroy(ainmf_handle h) {
     if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
     if (h->st_out) cudaStreamDestroy(h->st_out);
+    if (h->st_aux) { cudaStreamDestroy(h->st_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->poll_host) cudaFreeHost(h->poll_host);
     delete h;
@@ -818,8 +830,8 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     // Chunk schedule.  A chunk costs a fixed ~8 ms (200 iterations x launch gaps, fill and drain of six kernels) whatever its
     // size, so few large chunks beat many small ones; what stays exposed is the copy-in of the first chunk and the copy-out
     // of the last.  So: a first chunk of n_sm clips (one clip per SM in every round of the persistent kernels, the smallest
-    // size that still runs at ~95 % of the large-batch rate; 4.7 ms of copy-in at 10 s clips), then the rest in equal
-    // chunks as large as memory and the 512-clip cap allow.  512 clips: [148, 364] (measured against [148, 148, 148, 68],
+    // size that still runs at ~95 % of the large-batch rate; 4.7 ms of copy-in at 10 s clips), then chunks as large as
+    // memory and the 512-clip cap allow.  512 clips: [148, 364]; 4096: [148, 8 x 444, 396] (measured against [148, 148, 148, 68],
     // [148, 216, 148], [148, 296, 68], [222, 290], [296, 216], [74, 438]: profiles/r02e_e2e_chunk_schedules.txt).
     std::vector<long long> c_begin;          // first clip of every chunk, then the batch size
     long long chunk = 0;                     // clips in the largest chunk
@@ -842,9 +854,19 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         c_begin.push_back(0);
         const long long done = first < p->batch ? first : p->batch;
         c_begin.push_back(done);
-        if (p->batch > done) {
-            const long long rest = p->batch - done, n = (rest + cap - 1) / cap;
-            for (long long i = 1; i <= n; ++i) c_begin.push_back(done + rest * i / n);
+        // the kernels hand out per-clip items to n_sm (or 2 n_sm) CTAs: a chunk of m x n_sm clips fills every round, 444 clips
+        // cost 0.574 ms each where 494 cost 0.591 and 512 0.587.  What is left at the end goes with the last chunk if the cap
+        // allows (a tail of 68 clips runs at 0.9 ms per clip), else the last multiple is shortened to leave n_sm or more.
+        const long long sm = h->n_sm, mult = cap >= sm ? cap / sm * sm : cap;
+        for (long long at = done; at < p->batch;) {
+            const long long left = p->batch - at;
+            long long take_n = left;
+            if (left > cap) {
+                take_n = mult;
+                if (left - take_n < sm && take_n > sm) take_n -= sm;
+            }
+            at += take_n;
+            c_begin.push_back(at);
         }
         chunk = 0;
         for (size_t i = 0; i + 1 < c_begin.size(); ++i) if (c_begin[i + 1] - c_begin[i] > chunk) chunk = c_begin[i + 1] - c_begin[i];

@@ -202,6 +202,10 @@ struct NmfWork {
     char* coop_scratch = nullptr;       // 4 KB: grid-barrier word + per-CTA violation shares of the one-clip cooperative fit
     float* kl_sums = nullptr;           // MU-KL: [2][B][KP] row sums of H, column sums of W (the denominators)
     double* kl_err = nullptr;           // MU-KL: [B] final divergence (kept across nmf_finalize, which reports the Frobenius error)
+    // side stream for the small reductions that depend only on Ht (hbad): they run next to the X.Ht kernel instead of
+    // after it.  Null: everything on the caller's stream.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 enum { NMF_PHASE_PARTIALS = 1, NMF_PHASE_UPDATE = 2, NMF_PHASE_STOP = 4,
        NMF_PHASE_STOP_PACKED = 8 };   // with STOP: the H-side violation is read from wk.h_viol_pack (summed hi + lo floats)

@@ -683,13 +683,27 @@ static cudaError_t iterate_impl(const NmfProblem& p, const NmfWork& wk, int it, 
     const int S = wk.use_tc ? wk.tc_splits : ceil_div(p.T, fps);
     if ((phases & NMF_PHASE_PARTIALS) && wk.use_tc) {
         // tensor-core path: one kernel yields the X.Ht partials and the Gram of Ht
+        // hbad reads Ht only, like the X.Ht kernel: with a side stream its two small launches (latency-bound, a few blocks
+        // per clip) share the SMs with the persistent X.Ht kernel (one CTA of 512 threads per SM leaves room for them)
+        // instead of adding their 13 us to every iteration
+        const bool fork = p.t_good && wk.aux_stream;
+        cudaStream_t hs = fork ? wk.aux_stream : s;
+        auto launch_hbad = [&]() -> cudaError_t {
+            AINMF_LAUNCH(hbad_kernel, dim3(wk.hbad_blocks, p.B), dim3(kThreads), 0, hs, p.Ht, p.h_stride, p.T, KP, p.t_good, wk.tc_hbad_part,
+                         p.state);
+            AINMF_LAUNCH(hbad_reduce_kernel, dim3(p.B), dim3(128), 0, hs, wk.tc_hbad_part, wk.hbad_blocks, KP, wk.tc_hbad, p.state);
+            return cudaGetLastError();
+        };
+        if (fork) {
+            if ((e = cudaEventRecord(wk.ev_fork, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(hs, wk.ev_fork, 0)) != cudaSuccess) return e;
+        }
         prof_begin(PROF_XHT, s);
         if ((e = nmf_tc_half1(p, wk, s)) != cudaSuccess) return e;
-        if (p.t_good) {
-            AINMF_LAUNCH(hbad_kernel, dim3(wk.hbad_blocks, p.B), dim3(kThreads), 0, s, p.Ht, p.h_stride, p.T, KP, p.t_good, wk.tc_hbad_part,
-                         p.state);
-            AINMF_LAUNCH(hbad_reduce_kernel, dim3(p.B), dim3(128), 0, s, wk.tc_hbad_part, wk.hbad_blocks, KP, wk.tc_hbad, p.state);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (p.t_good && (e = launch_hbad()) != cudaSuccess) return e;
+        if (fork) {
+            if ((e = cudaEventRecord(wk.ev_join, hs)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(s, wk.ev_join, 0)) != cudaSuccess) return e;
         }
         prof_end(PROF_XHT, s);
         if (wk.xht_reduced) {
