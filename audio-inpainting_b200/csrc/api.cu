@@ -373,6 +373,19 @@ __global__ void copy_indices_kernel(const int* __restrict__ idx, const ClipState
 // but the host looks at the answer of group g only after it has queued group g + 1: the stream never drains while the host
 // waits and launches.  Kernels skip clips whose stop rule fired (ClipState.done, set on the device), so the up to `poll`
 // extra iterations queued after the last clip converged do nothing and every clip's n_iter is exact.
+// Side stream of the coordinate-descent iteration (tensor-core path, good-first frame order): hbad_kernel and its reduce
+// read Ht only, as the X.Ht kernel does, and run next to it (iterate_impl forks and joins with the two events).
+int attach_aux_stream(ainmf_handle h, const NmfProblem& prob, NmfWork* nw) {
+    if (!nw->use_tc || !prob.t_good || getenv("AINMF_NO_AUX_STREAM")) return 0;
+    if (!h->st_aux) {
+        CU(h, cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking));
+        CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    nw->aux_stream = h->st_aux; nw->ev_fork = h->ev_fork; nw->ev_join = h->ev_join;
+    return 0;
+}
+
 int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, int max_iter, float tol, int* d_flag,
                    cudaStream_t s) {
     const bool kl = prob.solver == AINMF_SOLVER_MU_KL;
@@ -389,14 +402,7 @@ int run_iterations(ainmf_handle h, const NmfProblem& prob, const NmfWork& nw, in
     if (tol > 0.f && !h->ev_poll[0])
         for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
     NmfWork nwf = nw;                      // with the side stream for the reductions that run next to the X.Ht kernel
-    if (!mu && nw.use_tc && prob.t_good && !getenv("AINMF_NO_AUX_STREAM")) {
-        if (!h->st_aux) {
-            CU(h, cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking));
-            CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        }
-        nwf.aux_stream = h->st_aux; nwf.ev_fork = h->ev_fork; nwf.ev_join = h->ev_join;
-    }
+    if (!mu && attach_aux_stream(h, prob, &nwf)) return AINMF_ERR_CUDA;
     int pending = -1;
     for (int it = 1; it <= max_iter; ++it) {
         if (kl) CU(h, nmf_mukl_iterate(prob, nw, it, s));

@@ -11,7 +11,9 @@
  *
  * Conventions
  *   - every data pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers;
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*) or on a side stream of the handle that forks
+ *     from and joins back into `stream` inside the call (event-ordered, invisible to the caller: whatever is enqueued on
+ *     `stream` after the call runs after all of it); nothing synchronises unless stated;
  *   - return value: 0 on success, negative ainmf_status otherwise; text via ainmf_last_error();
  *   - no CPU fallback exists: without a CUDA device ainmf_create fails;
  *   - threads and streams: a handle owns scratch memory, pinned staging, cached FFT / window / N(0,1) tables and the
