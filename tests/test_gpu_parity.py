@@ -415,6 +415,17 @@ def test_good_first_frame_order_skips_bad_frames_exactly(ops):
         assert int(nb1[b]) == len(st["bad"])
         assert abs(float(e1[b]) - st["err"]) <= 1e-4 * st["err"]
         assert libcalls.snr_db(yo, y1[b].cpu().numpy()) >= 60.0
+    # the sum of the bad frames' rows of Ht runs on a side stream of the handle next to the X.Ht kernel (forked and joined
+    # with events every iteration): same kernels, same order of additions -> bit-identical to the one-stream schedule, run
+    # after run (a lost dependency between the two streams would show up here as a difference)
+    os.environ["AINMF_NO_AUX_STREAM"] = "1"
+    try:
+        y2, idx2, nb2, W2, H2, e2, n2 = ops.nmf_inpaint(dev(X), *args)
+    finally:
+        os.environ.pop("AINMF_NO_AUX_STREAM", None)
+    for _ in range(3):
+        y3, idx3, nb3, W3, H3, e3, n3 = ops.nmf_inpaint(dev(X), *args)
+        assert torch.equal(y3, y2) and torch.equal(W3, W2) and torch.equal(H3, H2) and torch.equal(e3, e2) and torch.equal(n3, n2)
 
 
 def test_no_bad_frames_returns_input(ops):
