@@ -815,10 +815,15 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
     return AINMF_OK;
 }
 
-int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, int32_t* n_bad_host,
-                       float* err_host, int32_t* n_iter_host, size_t max_device_bytes) {
-    if (!h) return AINMF_ERR_INVALID;
-    if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
+}  // extern "C"
+
+namespace {
+// ainmf_inpaint_host (channels == 0: float32 in x_host / y_host) and ainmf_inpaint_host_pcm16 (channels >= 1: interleaved
+// int16 in pcm_in_host, int16 in pcm_out_host; the chunk is converted on the device either side of the fit, pcm.cu)
+int inpaint_host_impl(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, const int16_t* pcm_in_host,
+                      int channels, int16_t* pcm_out_host, float* peak_host, int32_t* n_bad_host, float* err_host,
+                      int32_t* n_iter_host, size_t max_device_bytes) {
+    const bool pcm = channels > 0;
     const auto t_call = std::chrono::steady_clock::now();
     CU(h, cudaSetDevice(h->device));
     // workspace per clip, estimated on a batch large enough to include what only big batches allocate (the permuted copy
@@ -829,7 +834,8 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     if (probe_ws == 0) return AINMF_ERR_INVALID;       // message set by make_plan
     const size_t per_clip_ws = (probe_ws + one.batch - 1) / one.batch;
     const long long N = p->n_samples;
-    const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256;
+    const size_t per_clip = per_clip_ws + 4 * sizeof(float) * (size_t)N + 256 +
+                            (pcm ? 2 * sizeof(int16_t) * (size_t)N * (channels + 1) + 64 : 0);
     // Clips go through in chunks, two in flight: while chunk c is being fitted, chunk c+1 arrives on the copy-in stream and
     // the result of chunk c-1 leaves on the copy-out stream (x and y double-buffered, one workspace).  A chunk is at most 512
     // clips (and what device memory allows).
@@ -843,6 +849,7 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     long long chunk = 0;                     // clips in the largest chunk
     ainmf_params cp = *p;
     size_t ws = 0, o = 0, oX[2], oY[2], oNb[2], oEr[2], oNi[2], oWs = 0;
+    size_t oPi[2] = {0, 0}, oPo[2] = {0, 0}, oPk[2] = {0, 0}, oPb = 0;     // 16-bit form: interleaved input, output, peaks; peak scratch
     auto schedule = [&](long long cap) {     // chunks of at most cap clips, and the scratch layout that holds them
         if (cap > 512) cap = 512;
         if (cap > p->batch) cap = p->batch;
@@ -885,6 +892,13 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
             oNb[i] = take(sizeof(int) * chunk); oEr[i] = take(sizeof(float) * chunk); oNi[i] = take(sizeof(int) * chunk);
         }
         oWs = take(ws);
+        if (pcm) {
+            for (int i = 0; i < 2; ++i) {
+                oPi[i] = take(sizeof(int16_t) * chunk * N * channels); oPo[i] = take(sizeof(int16_t) * chunk * N);
+                oPk[i] = take(sizeof(float) * chunk);
+            }
+            oPb = take(sizeof(int) * chunk);
+        }
     };
     if (max_device_bytes == 0) {
 #ifndef AINMF_EMU
@@ -921,10 +935,11 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         }
     }
     void* pin;
-    if ((rc = get_pinned(h, 3 * sizeof(int) * (size_t)p->batch, &pin))) return rc;
+    if ((rc = get_pinned(h, 4 * sizeof(int) * (size_t)p->batch, &pin))) return rc;
     int* stage_nb = (int*)pin;
     float* stage_er = (float*)(stage_nb + p->batch);
     int* stage_ni = (int*)(stage_er + p->batch);
+    float* stage_pk = (float*)(stage_ni + p->batch);
     const long long n_chunks = (long long)c_begin.size() - 1;
     auto chunk_size = [&](long long c) { return (int)(c_begin[c + 1] - c_begin[c]); };
     const bool trace = getenv("AINMF_HOST_TRACE") != nullptr;   // host wall-clock of the phases, device time of every chunk's copies and fit
@@ -934,7 +949,8 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         const int j = (int)(c & 1);
         if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_in, h->ev_done[j], 0));       // the fit of chunk c-2 has read this x buffer
         mark(cev, h->st_in);
-        CU(h, cudaMemcpyAsync(base + oX[j], x_host + c_begin[c] * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
+        if (pcm) CU(h, cudaMemcpyAsync(base + oPi[j], pcm_in_host + c_begin[c] * N * channels, sizeof(int16_t) * (size_t)chunk_size(c) * N * channels, cudaMemcpyHostToDevice, h->st_in));
+        else CU(h, cudaMemcpyAsync(base + oX[j], x_host + c_begin[c] * N, sizeof(float) * (size_t)chunk_size(c) * N, cudaMemcpyHostToDevice, h->st_in));
         mark(cev, h->st_in);
         CU(h, cudaEventRecord(h->ev_in[j], h->st_in));
         return 0;
@@ -953,14 +969,22 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_in[j], 0));
         if (c >= 2) CU(h, cudaStreamWaitEvent(h->st_cmp, h->ev_out[j], 0));        // the result of chunk c-2 has left this y buffer
         mark(tev, h->st_cmp);
+        if (pcm)      // load_damaged_data on the device: channel mean, peak, exact division (the x buffer is free: chunk c-2's fit is over)
+            CU(h, launch_load_pcm16((const int16_t*)(base + oPi[j]), nb, N, channels, (float*)(base + oX[j]), (int*)(base + oPb), (float*)(base + oPk[j]), h->st_cmp));
         rc = ainmf_inpaint(h, &cp, (const float*)(base + oX[j]), nullptr, nullptr, (float*)(base + oY[j]), nullptr,
                            (int*)(base + oNb[j]), nullptr, nullptr, (float*)(base + oEr[j]), (int*)(base + oNi[j]), base + oWs, ws, h->st_cmp);
         if (rc) break;
+        if (pcm) CU(h, launch_store_pcm16((const float*)(base + oY[j]), (long long)nb * N, (int16_t*)(base + oPo[j]), h->st_cmp));   // save_result
         mark(tev, h->st_cmp);
         CU(h, cudaEventRecord(h->ev_done[j], h->st_cmp));
         CU(h, cudaStreamWaitEvent(h->st_out, h->ev_done[j], 0));
         mark(oev, h->st_out);
-        CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY[j], sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
+        if (pcm) {
+            CU(h, cudaMemcpyAsync(pcm_out_host + b0 * N, base + oPo[j], sizeof(int16_t) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
+            CU(h, cudaMemcpyAsync(stage_pk + b0, base + oPk[j], sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st_out));
+        } else {
+            CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY[j], sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
+        }
         // the per-clip scalars go through pinned staging: a copy into the caller's (pageable) arrays would block this thread
         // until the fit and the copy-out of this chunk are over, and nothing of the next chunk would be queued meanwhile
         CU(h, cudaMemcpyAsync(stage_nb + b0, base + oNb[j], sizeof(int) * nb, cudaMemcpyDeviceToHost, h->st_out));
@@ -993,8 +1017,27 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
         if (n_bad_host) memcpy(n_bad_host, stage_nb, sizeof(int) * (size_t)p->batch);
         if (err_host) memcpy(err_host, stage_er, sizeof(float) * (size_t)p->batch);
         if (n_iter_host) memcpy(n_iter_host, stage_ni, sizeof(int) * (size_t)p->batch);
+        if (pcm && peak_host) memcpy(peak_host, stage_pk, sizeof(float) * (size_t)p->batch);
     }
     return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, int32_t* n_bad_host,
+                       float* err_host, int32_t* n_iter_host, size_t max_device_bytes) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
+    return inpaint_host_impl(h, p, x_host, y_host, nullptr, 0, nullptr, nullptr, n_bad_host, err_host, n_iter_host, max_device_bytes);
+}
+
+int ainmf_inpaint_host_pcm16(ainmf_handle h, const ainmf_params* p, const int16_t* pcm_host, int32_t channels, int16_t* out_host,
+                             float* peak_host, int32_t* n_bad_host, float* err_host, int32_t* n_iter_host, size_t max_device_bytes) {
+    if (!h) return AINMF_ERR_INVALID;
+    if (!p || !pcm_host || !out_host) return fail(h, AINMF_ERR_INVALID, "params, pcm_host and out_host must not be NULL");
+    if (channels < 1 || channels > 8) return fail(h, AINMF_ERR_INVALID, "channels must be in [1,8], got %d", channels);
+    return inpaint_host_impl(h, p, nullptr, nullptr, pcm_host, channels, out_host, peak_host, n_bad_host, err_host, n_iter_host, max_device_bytes);
 }
 
 unsigned long long ainmf_launch_count(void) { return ainmf::g_launch_count; }

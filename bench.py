@@ -487,6 +487,34 @@ def leg_clips(ctx, name, wl, steps, warmup, cpu_baseline=True, headline=False):
     torch.cuda.synchronize()
     e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
     ctx.barrier()
+    # ---- the same from 16-bit file samples to 16-bit file samples (ainmf_inpaint_host_pcm16): half the bytes over PCIe ----
+    e2e_pcm = None
+    if headline and B > 1:
+        ph = torch.empty((B, N), dtype=torch.int16).pin_memory()
+        ph.copy_((xh * 32767.0).to(torch.int16))
+        qh = torch.empty((B, N), dtype=torch.int16).pin_memory()
+        pkh = np.zeros(B, np.float32)
+
+        def pcm_step():
+            rc = L.ainmf_inpaint_host_pcm16(h, C.byref(p), C.c_void_p(ph.data_ptr()), 1, C.c_void_p(qh.data_ptr()),
+                                            pkh.ctypes.data_as(C.c_void_p), nbh.ctypes.data_as(C.c_void_p),
+                                            errh.ctypes.data_as(C.c_void_p), nih.ctypes.data_as(C.c_void_p), 0)
+            ctx.ainmf._lib.check(rc, ctx.local_rank)
+
+        for _ in range(warmup):
+            pcm_step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pcm_step()
+        torch.cuda.synchronize()
+        pcm_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        ctx.barrier()
+        e2e_pcm = {"value": ctx.world * B * N / SR * steps / (pcm_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": pcm_ms / steps,
+                   "h2d_bytes_per_step": B * N * 2, "d2h_bytes_per_step": B * N * 2 + B * 16,
+                   "api": "ainmf_inpaint_host_pcm16 (int16 samples in, int16 samples out; load_damaged_data and save_result on the device)",
+                   "iterations_done": int(nih.sum())}
+        del ph, qh
     audio_s_step = ctx.world * B * N / SR
     line = {
         "metric": "audio_seconds_restored_per_second", "value": audio_s_step * steps / (ms_total * 1e-3), "unit": "audio-s/s",
@@ -505,6 +533,8 @@ def leg_clips(ctx, name, wl, steps, warmup, cpu_baseline=True, headline=False):
                 "api": "ainmf_inpaint_host (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None, "parity": None,
     }
+    if e2e_pcm:
+        line["e2e_pcm16"] = e2e_pcm
     if ctx.rank == 0 and ctx.world == 1 and cpu_baseline:
         n_cpu = 8 if B > 1 else 1
         cores = use_all_host_threads()

@@ -145,6 +145,16 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
 int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, int32_t* n_bad_host,
                        float* err_host, int32_t* n_iter_host, size_t max_device_bytes);
 
+/* The same from file samples to file samples, the way the scripts run (main4_NMF_gap.py:17-26 load_damaged_data ->
+ * :42-72 restore -> :74-78 save_result): pcm_host [B][N][channels] interleaved int16 as scipy.io.wavfile.read returns
+ * it -> channel mean -> x / max|x| (ainmf_load_pcm16, bit-exact) -> ainmf_inpaint -> clip * 32767 truncated
+ * (ainmf_store_pcm16) -> out_host [B][N] int16 = what wavfile.write receives.  peak_host [B] (optional): max|x| before
+ * the normalisation.  Half the bytes of the float32 form cross PCIe in each direction; the conversions run on the device
+ * inside the chunk pipeline.  Pinned host buffers let the copies overlap the fits. */
+int ainmf_inpaint_host_pcm16(ainmf_handle h, const ainmf_params* p, const int16_t* pcm_host, int32_t channels,
+                             int16_t* out_host, float* peak_host, int32_t* n_bad_host, float* err_host,
+                             int32_t* n_iter_host, size_t max_device_bytes);
+
 /* ---- front/back end of the scripts ------------------------------------------------------ */
 /* load_damaged_data (main4_NMF_gap.py:21-24): int16 [B][N][channels] -> mono mean -> float32 -> x / max|x| (true
  * division).  peak [B] optional output. */

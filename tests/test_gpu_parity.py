@@ -547,6 +547,75 @@ def test_host_entry_point_pipelines_chunks_and_matches_the_device_op(ops):
     assert int((nbd == 0).sum()) >= 30 and int((nbd > 0).sum()) >= 200
 
 
+def test_host_entry_point_pcm16_is_the_file_to_file_path(ops, golden):
+    """ainmf_inpaint_host_pcm16: int16 samples as wavfile.read returns them -> int16 samples as wavfile.write receives them
+    (load_damaged_data -> restore -> save_result on the device, inside the chunk pipeline).  (1) The shipped damaged_gap.wav
+    gives the shipped fixed_nmf_gap.wav within 1 LSB outside the gap and 60 dB overall, the peak and the bad columns of the
+    reference.  (2) A 300-clip stereo batch (two chunks, some clips with nothing to restore) equals, sample for sample up to
+    1 LSB on at most 0.1 % of the samples, what the device ops give on the whole batch (load_pcm16 -> nmf_inpaint ->
+    store_pcm16; the chunked call uses other split factors, so the float sums differ in the last bits), and exactly for the
+    clips that have no bad frame."""
+    import ctypes as C
+    import ainmf
+    from ainmf import _capi
+    L = ainmf._lib.lib()
+    h = ainmf._lib.handle(0)
+    vp = C.c_void_p
+    # (1) the golden file
+    pcm = golden.gap_input_i16()
+    N = len(pcm)
+    pin = torch.from_numpy(pcm.copy()).pin_memory()
+    pout = torch.zeros(N, dtype=torch.int16).pin_memory()
+    peak, nb, er, ni = np.zeros(1, np.float32), np.zeros(1, np.int32), np.zeros(1, np.float32), np.zeros(1, np.int32)
+    p = _capi.default_params(L, batch=1, n_samples=N, n_fft=1024, hop=256, rank=40, max_iter=200, tol=1e-4, seed=42,
+                             threshold=1e-4, frac_num=9, frac_den=10)
+    rc = L.ainmf_inpaint_host_pcm16(h, C.byref(p), vp(pin.data_ptr()), 1, vp(pout.data_ptr()), peak.ctypes.data_as(vp),
+                                    nb.ctypes.data_as(vp), er.ctypes.data_as(vp), ni.ctypes.data_as(vp), 0)
+    ainmf._lib.check(rc, 0)
+    c2 = golden.c2
+    assert float(peak[0]) == float(np.max(np.abs(pcm))) and int(nb[0]) == len(c2["bad_cols"]) and int(ni[0]) == 200
+    assert abs(float(er[0]) - float(c2["err"])) <= 1e-4 * float(c2["err"])
+    q = pout.numpy().astype(np.int32)
+    shipped = pcm.astype(np.int32) + c2["shipped_minus_input_i16"]
+    gs, ge = c2["gap"]
+    outside = np.ones(N, bool)
+    outside[gs - 1024:ge + 1024] = False
+    assert np.max(np.abs(q[outside] - shipped[outside])) <= 1
+    assert libcalls.snr_db(shipped.astype(np.float64), q.astype(np.float64)) >= 60.0
+    # (2) a stereo batch in two chunks against the device ops
+    rng = np.random.default_rng(11)
+    B, N = 300, 12000
+    t = np.arange(N) / 8000.0
+    P = np.empty((B, N, 2), np.int16)
+    for b in range(B):
+        x = np.sin(2 * np.pi * rng.uniform(200, 1500) * t) + 0.3 * np.sin(2 * np.pi * rng.uniform(1500, 3500) * t) + 0.05 * rng.standard_normal(N)
+        x = x / np.abs(x).max() * rng.uniform(0.3, 0.95)
+        if b % 7 != 3:
+            s0 = int(rng.integers(500, N - 3000))
+            x[s0:s0 + int(rng.integers(300, 2000))] = 0
+        P[b, :, 0] = np.round(x * 32767).astype(np.int16)
+        P[b, :, 1] = np.round(0.8 * x * 32767).astype(np.int16)
+    xd, pkd = ops.load_pcm16(dev(P))
+    yd, idx, nbd, W, H, errd, nitd = ops.nmf_inpaint(xd, 256, 64, 16, 25, 0.0, 42, 1e-4, 9, 10, -1, -1, 1, None, None)
+    qd = ops.store_pcm16(yd).cpu().numpy()
+    pin = torch.from_numpy(P).pin_memory()
+    pout = torch.zeros((B, N), dtype=torch.int16).pin_memory()
+    peak, nb, er, ni = np.zeros(B, np.float32), np.zeros(B, np.int32), np.zeros(B, np.float32), np.zeros(B, np.int32)
+    p = _capi.default_params(L, batch=B, n_samples=N, n_fft=256, hop=64, rank=16, max_iter=25, tol=0.0, seed=42,
+                             threshold=1e-4, frac_num=9, frac_den=10)
+    for cap in (0, 40 << 20):
+        pout.zero_()
+        rc = L.ainmf_inpaint_host_pcm16(h, C.byref(p), vp(pin.data_ptr()), 2, vp(pout.data_ptr()), peak.ctypes.data_as(vp),
+                                        nb.ctypes.data_as(vp), er.ctypes.data_as(vp), ni.ctypes.data_as(vp), cap)
+        ainmf._lib.check(rc, 0)
+        assert np.array_equal(peak, pkd.cpu().numpy()) and np.array_equal(nb, nbd.cpu().numpy()) and np.array_equal(ni, nitd.cpu().numpy())
+        q = pout.numpy()
+        d = np.abs(q.astype(np.int32) - qd.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+        clean = nb == 0
+        assert clean.sum() >= 30 and np.array_equal(q[clean], qd[clean])
+
+
 def test_shim_classes_match_reference_interface(ops, golden, tmp_path):
     import ainmf
     from scipy.io import wavfile
