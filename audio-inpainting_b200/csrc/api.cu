@@ -111,6 +111,11 @@ struct ainmf_context {
     size_t pinned_bytes = 0;
     int* poll_host = nullptr;     // pinned
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};   // stop-flag polls, one group of iterations behind the launches
+    // last chunk of ainmf_inpaint_host: ainmf_inpaint runs the inverse STFT in four parts and sends each part's waveform to
+    // sink_y_host on sink_st as soon as it exists (the copy-out of the last chunk is the exposed one)
+    float* sink_y_host = nullptr;
+    cudaStream_t sink_st = nullptr;
+    cudaEvent_t ev_part[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st_aux = nullptr;                 // side stream of the iteration (hbad next to the X.Ht kernel) and its fork / join events
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // ainmf_inpaint_host pipeline: copy-in / compute / copy-out streams and the events that order two chunks in flight
@@ -484,6 +489,7 @@ int ainmf_destroy(ainmf_handle h) {
     if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
     if (h->st_out) cudaStreamDestroy(h->st_out);
+    for (int i = 0; i < 4; ++i) if (h->ev_part[i]) cudaEventDestroy(h->ev_part[i]);
     if (h->st_aux) { cudaStreamDestroy(h->st_aux); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->poll_host) cudaFreeHost(h->poll_host);
@@ -805,7 +811,18 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
         }
     }
     // a10 + a11: recombine with the corrupted phase, inverse STFT, trim
-    CU(h, launch_istft(V, Z, pl.vz_stride, bad, pl.bad_stride, d_nbad, x, N, 0, B, g, 0, T, tb, y, N, 0, N, T, s));
+    if (h->sink_y_host && B >= 8) {
+        for (int q = 0; q < 4; ++q) {
+            const long long b0 = (long long)B * q / 4, b1 = (long long)B * (q + 1) / 4;
+            CU(h, launch_istft(V + b0 * pl.vz_stride, Z + b0 * pl.vz_stride, pl.vz_stride, bad + b0 * pl.bad_stride, pl.bad_stride,
+                               d_nbad + b0, x + b0 * N, N, 0, (int)(b1 - b0), g, 0, T, tb, y + b0 * N, N, 0, N, T, s));
+            CU(h, cudaEventRecord(h->ev_part[q], s));
+            CU(h, cudaStreamWaitEvent(h->sink_st, h->ev_part[q], 0));
+            CU(h, cudaMemcpyAsync(h->sink_y_host + b0 * N, y + b0 * N, sizeof(float) * (size_t)(b1 - b0) * N, cudaMemcpyDeviceToHost, h->sink_st));
+        }
+    } else {
+        CU(h, launch_istft(V, Z, pl.vz_stride, bad, pl.bad_stride, d_nbad, x, N, 0, B, g, 0, T, tb, y, N, 0, N, T, s));
+    }
     if (bad_idx) {          // entries at and beyond n_bad are -1, whatever the workspace held
         AINMF_LAUNCH(copy_indices_kernel, dim3(ceil_div(T, kThreads), B), dim3(kThreads), 0, s, idx, st, T, bad_idx);
         CU(h, cudaGetLastError());
@@ -933,6 +950,7 @@ int inpaint_host_impl(ainmf_handle h, const ainmf_params* p, const float* x_host
             CU(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CU(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < 4; ++i) CU(h, cudaEventCreateWithFlags(&h->ev_part[i], cudaEventDisableTiming));
     }
     void* pin;
     if ((rc = get_pinned(h, 4 * sizeof(int) * (size_t)p->batch, &pin))) return rc;
@@ -971,18 +989,25 @@ int inpaint_host_impl(ainmf_handle h, const ainmf_params* p, const float* x_host
         mark(tev, h->st_cmp);
         if (pcm)      // load_damaged_data on the device: channel mean, peak, exact division (the x buffer is free: chunk c-2's fit is over)
             CU(h, launch_load_pcm16((const int16_t*)(base + oPi[j]), nb, N, channels, (float*)(base + oX[j]), (int*)(base + oPb), (float*)(base + oPk[j]), h->st_cmp));
+        // the last chunk's copy-out is the exposed one: its waveform leaves in four parts behind the parts of the inverse STFT
+        const bool sink = !pcm && c + 1 == n_chunks && nb >= 8 && !getenv("AINMF_HOST_NO_SINK");
+        if (sink) {
+            mark(oev, h->st_out);
+            h->sink_y_host = y_host + b0 * N; h->sink_st = h->st_out;
+        }
         rc = ainmf_inpaint(h, &cp, (const float*)(base + oX[j]), nullptr, nullptr, (float*)(base + oY[j]), nullptr,
                            (int*)(base + oNb[j]), nullptr, nullptr, (float*)(base + oEr[j]), (int*)(base + oNi[j]), base + oWs, ws, h->st_cmp);
+        h->sink_y_host = nullptr; h->sink_st = nullptr;
         if (rc) break;
         if (pcm) CU(h, launch_store_pcm16((const float*)(base + oY[j]), (long long)nb * N, (int16_t*)(base + oPo[j]), h->st_cmp));   // save_result
         mark(tev, h->st_cmp);
         CU(h, cudaEventRecord(h->ev_done[j], h->st_cmp));
         CU(h, cudaStreamWaitEvent(h->st_out, h->ev_done[j], 0));
-        mark(oev, h->st_out);
+        if (!sink) mark(oev, h->st_out);
         if (pcm) {
             CU(h, cudaMemcpyAsync(pcm_out_host + b0 * N, base + oPo[j], sizeof(int16_t) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
             CU(h, cudaMemcpyAsync(stage_pk + b0, base + oPk[j], sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st_out));
-        } else {
+        } else if (!sink) {
             CU(h, cudaMemcpyAsync(y_host + b0 * N, base + oY[j], sizeof(float) * (size_t)nb * N, cudaMemcpyDeviceToHost, h->st_out));
         }
         // the per-clip scalars go through pinned staging: a copy into the caller's (pageable) arrays would block this thread
