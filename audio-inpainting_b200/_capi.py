@@ -15,6 +15,7 @@ EXPORTS = [
     "ainmf_inpaint_sharded", "ainmf_launch_count", "ainmf_profile", "ainmf_comm_set_callbacks",
     "ainmf_find_main_gap", "ainmf_find_gaps", "ainmf_linear_interp", "ainmf_blend_boundaries", "ainmf_snr_db", "ainmf_apply_gaps",
     "ainmf_set_window", "ainmf_standard_normal", "ainmf_comm_transport", "ainmf_inpaint_host_pcm16",
+    "ainmf_host_chunk_schedule",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
@@ -50,6 +51,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "ainmf_inpaint": (C.c_int, [vp, P(Params), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "ainmf_inpaint_host": (C.c_int, [vp, P(Params), vp, vp, vp, vp, vp, sz]),
         "ainmf_inpaint_host_pcm16": (C.c_int, [vp, P(Params), vp, i32, vp, vp, vp, vp, vp, sz]),
+        "ainmf_host_chunk_schedule": (C.c_int, [i64, i64, i32, vp, i32, vp]),
         "ainmf_load_pcm16": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),
         "ainmf_store_pcm16": (C.c_int, [vp, vp, i64, vp, vp]),
         "ainmf_find_main_gap": (C.c_int, [vp, vp, i32, i64, f32, vp, vp]),

@@ -835,6 +835,40 @@ int ainmf_inpaint(ainmf_handle h, const ainmf_params* p, const float* x, const f
 }  // extern "C"
 
 namespace {
+// Chunk schedule of the host entry points (see inpaint_host_impl): c_begin = first clip of every chunk, then the batch size.
+void plan_host_chunks(long long batch, long long cap, long long n_sm, std::vector<long long>* c_begin) {
+    if (cap > 512) cap = 512;
+    if (cap > batch) cap = batch;
+    long long first = cap;
+    if (batch >= 2 * n_sm && cap >= 2 * n_sm) first = n_sm;
+    if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk, all equal
+        const long long v = atoll(ev);
+        if (v >= 1 && v < cap) first = cap = v;
+    }
+    if (const char* ev = getenv("AINMF_HOST_FIRST")) {      // development switch: clips in the first chunk
+        const long long v = atoll(ev);
+        if (v >= 1 && v <= cap) first = v;
+    }
+    c_begin->clear();
+    c_begin->push_back(0);
+    const long long done = first < batch ? first : batch;
+    c_begin->push_back(done);
+    // the kernels hand out per-clip items to n_sm (or 2 n_sm) CTAs: a chunk of m x n_sm clips fills every round, 444 clips
+    // cost 0.574 ms each where 494 cost 0.591 and 512 0.587.  What is left at the end goes with the last chunk if the cap
+    // allows (a tail of 68 clips runs at 0.9 ms per clip), else the last multiple is shortened to leave n_sm or more.
+    const long long sm = n_sm, mult = cap >= sm ? cap / sm * sm : cap;
+    for (long long at = done; at < batch;) {
+        const long long left = batch - at;
+        long long take_n = left;
+        if (left > cap) {
+            take_n = mult;
+            if (left - take_n < sm && take_n > sm) take_n -= sm;
+        }
+        at += take_n;
+        c_begin->push_back(at);
+    }
+}
+
 // ainmf_inpaint_host (channels == 0: float32 in x_host / y_host) and ainmf_inpaint_host_pcm16 (channels >= 1: interleaved
 // int16 in pcm_in_host, int16 in pcm_out_host; the chunk is converted on the device either side of the fit, pcm.cu)
 int inpaint_host_impl(ainmf_handle h, const ainmf_params* p, const float* x_host, float* y_host, const int16_t* pcm_in_host,
@@ -868,36 +902,7 @@ int inpaint_host_impl(ainmf_handle h, const ainmf_params* p, const float* x_host
     size_t ws = 0, o = 0, oX[2], oY[2], oNb[2], oEr[2], oNi[2], oWs = 0;
     size_t oPi[2] = {0, 0}, oPo[2] = {0, 0}, oPk[2] = {0, 0}, oPb = 0;     // 16-bit form: interleaved input, output, peaks; peak scratch
     auto schedule = [&](long long cap) {     // chunks of at most cap clips, and the scratch layout that holds them
-        if (cap > 512) cap = 512;
-        if (cap > p->batch) cap = p->batch;
-        long long first = cap;
-        if (p->batch >= 2 * h->n_sm && cap >= 2 * h->n_sm) first = h->n_sm;
-        if (const char* ev = getenv("AINMF_HOST_CHUNK")) {      // development switch: clips per chunk, all equal
-            const long long v = atoll(ev);
-            if (v >= 1 && v < cap) first = cap = v;
-        }
-        if (const char* ev = getenv("AINMF_HOST_FIRST")) {      // development switch: clips in the first chunk
-            const long long v = atoll(ev);
-            if (v >= 1 && v <= cap) first = v;
-        }
-        c_begin.clear();
-        c_begin.push_back(0);
-        const long long done = first < p->batch ? first : p->batch;
-        c_begin.push_back(done);
-        // the kernels hand out per-clip items to n_sm (or 2 n_sm) CTAs: a chunk of m x n_sm clips fills every round, 444 clips
-        // cost 0.574 ms each where 494 cost 0.591 and 512 0.587.  What is left at the end goes with the last chunk if the cap
-        // allows (a tail of 68 clips runs at 0.9 ms per clip), else the last multiple is shortened to leave n_sm or more.
-        const long long sm = h->n_sm, mult = cap >= sm ? cap / sm * sm : cap;
-        for (long long at = done; at < p->batch;) {
-            const long long left = p->batch - at;
-            long long take_n = left;
-            if (left > cap) {
-                take_n = mult;
-                if (left - take_n < sm && take_n > sm) take_n -= sm;
-            }
-            at += take_n;
-            c_begin.push_back(at);
-        }
+        plan_host_chunks(p->batch, cap, h->n_sm, &c_begin);
         chunk = 0;
         for (size_t i = 0; i + 1 < c_begin.size(); ++i) if (c_begin[i + 1] - c_begin[i] > chunk) chunk = c_begin[i + 1] - c_begin[i];
         cp.batch = (int32_t)chunk;
@@ -1055,6 +1060,17 @@ int ainmf_inpaint_host(ainmf_handle h, const ainmf_params* p, const float* x_hos
     if (!h) return AINMF_ERR_INVALID;
     if (!p || !x_host || !y_host) return fail(h, AINMF_ERR_INVALID, "params, x_host and y_host must not be NULL");
     return inpaint_host_impl(h, p, x_host, y_host, nullptr, 0, nullptr, nullptr, n_bad_host, err_host, n_iter_host, max_device_bytes);
+}
+
+int ainmf_host_chunk_schedule(int64_t batch, int64_t max_clips, int32_t n_sm, int32_t* sizes, int32_t max_sizes, int32_t* n_sizes) {
+    if (batch < 1 || max_clips < 1 || n_sm < 1 || !sizes || !n_sizes || max_sizes < 1) return AINMF_ERR_INVALID;
+    std::vector<long long> cb;
+    plan_host_chunks(batch, max_clips, n_sm, &cb);
+    const int n = (int)cb.size() - 1;
+    *n_sizes = n;
+    if (n > max_sizes) return AINMF_ERR_WORKSPACE;
+    for (int i = 0; i < n; ++i) sizes[i] = (int32_t)(cb[i + 1] - cb[i]);
+    return AINMF_OK;
 }
 
 int ainmf_inpaint_host_pcm16(ainmf_handle h, const ainmf_params* p, const int16_t* pcm_host, int32_t channels, int16_t* out_host,

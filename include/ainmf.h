@@ -155,6 +155,12 @@ int ainmf_inpaint_host_pcm16(ainmf_handle h, const ainmf_params* p, const int16_
                              int16_t* out_host, float* peak_host, int32_t* n_bad_host, float* err_host,
                              int32_t* n_iter_host, size_t max_device_bytes);
 
+/* The chunk schedule the two host entry points use for `batch` clips when at most `max_clips` fit the device at once
+ * (host logic only, no device needed): sizes[0..*n_sizes) clips per chunk, in order.  A first chunk of n_sm clips (short
+ * exposed copy-in), then multiples of n_sm up to min(max_clips, 512), what is left with the last chunk. */
+int ainmf_host_chunk_schedule(int64_t batch, int64_t max_clips, int32_t n_sm, int32_t* sizes, int32_t max_sizes,
+                              int32_t* n_sizes);
+
 /* ---- front/back end of the scripts ------------------------------------------------------ */
 /* load_damaged_data (main4_NMF_gap.py:21-24): int16 [B][N][channels] -> mono mean -> float32 -> x / max|x| (true
  * division).  peak [B] optional output. */

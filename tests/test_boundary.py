@@ -35,6 +35,34 @@ def test_header_symbols_are_exported(lib):
         assert hasattr(lib, n), n
 
 
+def test_host_chunk_schedule(lib):
+    """Host logic of ainmf_inpaint_host / _pcm16: every clip in exactly one chunk, no chunk above the cap, a first chunk of
+    one clip per SM when the batch holds two such chunks, multiples of the SM count in the middle, no short tail."""
+    import ctypes as C
+    import numpy as np
+
+    def sched(batch, cap, sm=148):
+        sizes = np.zeros(4096, np.int32)
+        n = C.c_int32(0)
+        assert lib.ainmf_host_chunk_schedule(batch, cap, sm, sizes.ctypes.data_as(C.c_void_p), len(sizes), C.byref(n)) == 0
+        return sizes[:n.value].tolist()
+
+    assert sched(1, 512) == [1] and sched(100, 512) == [100] and sched(295, 512) == [295]
+    assert sched(296, 512) == [148, 148] and sched(300, 512) == [148, 152]
+    assert sched(512, 512) == [148, 364]                                   # the bench's batch
+    assert sched(4096, 512) == [148] + [444] * 8 + [396]
+    assert sched(668, 512) == [148, 296, 224]                              # 444 would leave a tail of 76
+    assert sched(300, 17) == [17] * 17 + [11]                              # memory cap below one clip per SM
+    assert lib.ainmf_host_chunk_schedule(0, 512, 148, None, 0, None) != 0
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        batch, cap, sm = int(rng.integers(1, 6000)), int(rng.integers(1, 700)), int(rng.choice([8, 132, 148, 160]))
+        s = sched(batch, cap, sm)
+        assert sum(s) == batch and min(s) >= 1 and max(s) <= min(cap, 512), (batch, cap, sm, s)
+        if cap >= 2 * sm and batch >= 2 * sm:
+            assert s[0] == sm and all(c % sm == 0 for c in s[1:-1]) and s[-1] >= min(sm, batch - sm), (batch, cap, sm, s)
+
+
 def test_version_and_defaults(lib):
     import ainmf
     assert b"sm_100a" in lib.ainmf_version()
